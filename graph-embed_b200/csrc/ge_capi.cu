@@ -1,0 +1,519 @@
+// graph-embed_b200 :: the C ABI (include/graph_embed_b200.h) and the host-side level driver.
+//
+// Host logic restated here, from scratch, for the drop-in:
+//   ge_embed        <- partition::embed / embedMultilevel, /root/reference/src/embed.cpp:561-796
+//   level_radii     <- the ball-radius and rescale step, src/embed.cpp:615-778
+//   reference_uniform <- the reference's generator, include/forceatlas.hpp:104-108
+// Everything numerical that iterates runs on the device; there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ge_context.h"
+
+namespace ge {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+uint32_t resolve_seed(uint32_t seed) {
+  if (seed != 0) return seed;
+  std::random_device rd;  // what the reference does for every generator
+  return rd();
+}
+
+void reference_uniform(uint32_t seed, int64_t count, double* out) {
+  std::mt19937 gen(seed);
+  std::uniform_real_distribution<double> random(-1.0, 1.0);
+  for (int64_t c = 0; c < count; ++c) out[c] = random(gen);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ball radii (src/embed.cpp:615-778).  Every pair (base case) or intra-super-aggregate coarse
+// edge (general case) is an event "the two growing balls touch" at time -t; events are served
+// latest-key-first in the lexicographic (t, i, j) order the reference obtains by sorting a
+// vector of tuples and popping its back.  A max-heap gives the same service order without the
+// reference's full re-sort after every freeze.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Event {
+  double t;
+  int i, j;
+  bool operator<(const Event& o) const { return std::tie(t, i, j) < std::tie(o.t, o.i, o.j); }
+};
+
+inline double dist(const double* a, const double* b, int dim) {
+  double sum = 0.0;
+  for (int k = 0; k < dim; ++k) {
+    const double d = b[k] - a[k];
+    sum += d * d;
+  }
+  return std::sqrt(sum);
+}
+
+void grow_balls(std::vector<Event>& ev, double* r_A, int m) {
+  std::make_heap(ev.begin(), ev.end());
+  int count = 0;
+  while (count < m && !ev.empty()) {
+    std::pop_heap(ev.begin(), ev.end());
+    const Event top = ev.back();
+    ev.pop_back();
+    const double reach = -top.t;
+    const bool live_i = r_A[top.i] <= 0.0, live_j = r_A[top.j] <= 0.0;
+    if (!live_i && !live_j) continue;
+    const int fi = live_i ? top.i : -1, fj = live_j ? top.j : -1;
+    if (live_i) r_A[top.i] = reach;
+    if (live_j) r_A[top.j] = reach;
+    // a frozen ball stops growing: the partner must cover the remaining gap alone
+    for (Event& e : ev)
+      if (e.i == fi || e.j == fi || e.i == fj || e.j == fj) e.t = -(2 * (-e.t) - (-top.t));
+    std::make_heap(ev.begin(), ev.end());
+    count += (live_i ? 1 : 0) + (live_j ? 1 : 0);
+  }
+}
+}  // namespace
+
+void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
+                 const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac) {
+  std::fill(r_A, r_A + m, 0.0);
+  if (P_T_c == nullptr) {  // :616-679
+    std::vector<Event> ev;
+    ev.reserve((size_t)m * (m > 0 ? m - 1 : 0) / 2);
+    for (int i = 0; i < m; ++i)
+      for (int j = i + 1; j < m; ++j)
+        ev.push_back(Event{-dist(coords_A + (size_t)i * dim, coords_A + (size_t)j * dim, dim) / 2, i, j});
+    grow_balls(ev, r_A, m);
+    return;
+  }
+  const int mc = P_T_c->rows;
+  const int32_t* PI = P_T_c->indptr;
+  const int32_t* PJ = P_T_c->indices;
+  std::vector<int> parent(m, -1);  // :684
+  for (int b = 0; b < mc; ++b)
+    for (int c = PI[b]; c < PI[b + 1]; ++c) parent[PJ[c]] = b;
+  std::vector<Event> ev;
+  for (int b = 0; b < mc; ++b) {  // :686-756 (independent per super-aggregate)
+    const int s = PI[b + 1] - PI[b];
+    if (s == 1) {
+      r_A[PJ[PI[b]]] = r_Ac[b];
+      continue;
+    }
+    ev.clear();
+    for (int c = PI[b]; c < PI[b + 1]; ++c) {
+      const int a = PJ[c];
+      for (int kk = A_c->indptr[a]; kk < A_c->indptr[a + 1]; ++kk) {
+        const int j = A_c->indices[kk];
+        if (a < j && parent[j] == parent[a])
+          ev.push_back(Event{-dist(coords_A + (size_t)a * dim, coords_A + (size_t)j * dim, dim) / 2, a, j});
+      }
+    }
+    grow_balls(ev, r_A, m);
+  }
+  for (int b = 0; b < mc; ++b) {  // :757-777 shrink each family into its parent ball
+    const double* cb = coords_Ac + (size_t)b * dim;
+    double alpha = 0.0;
+    for (int c = PI[b]; c < PI[b + 1]; ++c) {
+      const int a = PJ[c];
+      alpha = std::max(alpha, dist(cb, coords_A + (size_t)a * dim, dim) + r_A[a]);
+    }
+    if (alpha < 0.000001) alpha = 0.000001;
+    const double scale = r_Ac[b] / alpha;
+    for (int c = PI[b]; c < PI[b + 1]; ++c) {
+      const int a = PJ[c];
+      for (int k = 0; k < dim; ++k)
+        coords_A[(size_t)a * dim + k] = cb[k] + scale * (coords_A[(size_t)a * dim + k] - cb[k]);
+      r_A[a] = scale * r_A[a];
+    }
+  }
+}
+
+namespace {
+
+int onchip_threshold() {
+  const char* v = std::getenv("GE_ONCHIP_MAX");
+  return v ? std::min(std::atoi(v), kOnchipMaxVertices) : 256;
+}
+
+void check_csr(const ge_csr* A, const char* what) {
+  GE_REQUIRE(A != nullptr, std::string(what) + " is null");
+  GE_REQUIRE(A->rows >= 0 && A->cols >= 0, std::string(what) + " has negative shape");
+  GE_REQUIRE(A->indptr != nullptr, std::string(what) + ".indptr is null");
+  GE_REQUIRE(A->indptr[A->rows] == 0 || A->indices != nullptr, std::string(what) + ".indices is null");
+  GE_REQUIRE((int64_t)A->indptr[A->rows] == A->nnz, std::string(what) + ".nnz != indptr[rows]");
+}
+
+void flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const ge_params& p,
+                int path) {
+  const bool onchip = path == 2 || (path == 0 && A.rows <= onchip_threshold());
+  if (A.rows == 0) return;
+  if (onchip) {
+    onchip_flat_solve(ctx, A, dim, p, coords, nullptr, false);
+    return;
+  }
+  std::unique_ptr<FlatSolver> s(make_flat_solver(ctx, A, dim, p, 0, A.rows));
+  s->upload_coords(coords);
+  for (int it = 0; it < p.iterations; ++it) {
+    s->launch_iteration(true);
+    s->swap();
+  }
+  if (p.normalize) s->normalize();
+  s->download_coords(coords);
+}
+
+struct LevelOut {
+  std::vector<double> coords, r_A, coords_A;
+};
+
+struct EmbedRun {
+  ge_context* ctx;
+  int L, dim;
+  const ge_csr* As;
+  const ge_csr* Ps;
+  ge_embed_options opt;
+  ge_embed_stats st{};
+
+  // embedMultilevel, src/embed.cpp:576-796.  Returns this level's coordinates; r_A / coords_A
+  // receive the radii and (rescaled) coordinates of level+1, as the reference's out-params do.
+  std::vector<double> level(int l, std::vector<double>& r_A, std::vector<double>& coords_A) {
+    const ge_csr& A = As[l];
+    const int n = A.rows;
+    if (l == L) {  // :582-587
+      if (opt.verbose) std::printf("embedding layer %d: getting base coords\n", l + 1);
+      r_A.clear();
+      coords_A.clear();
+      std::vector<double> coords((size_t)n * dim);
+      reference_uniform(resolve_seed(opt.seed), (int64_t)n * dim, coords.data());  // forceatlas.hpp:118-125
+      ge_params p;
+      ge_params_default_flat(&p);
+      p.iterations = opt.coarse_iterations;
+      p.precision = opt.precision;
+      const double t0 = now_ms();
+      flat_solve(ctx, A, dim, coords.data(), p, 0);
+      st.coarse_ms += now_ms() - t0;
+      st.pair_interactions += double(n) * double(n - 1) * p.iterations;
+      st.edge_visits += double(A.nnz) * p.iterations;
+      return coords;
+    }
+    std::vector<double> r_Ac, coords_Ac;
+    coords_A = level(l + 1, r_Ac, coords_Ac);  // :593
+    const ge_csr& P = Ps[l];
+    const int m = P.rows;
+    if (opt.verbose) std::printf("embeding layer %d\n", l + 1);
+    const double t0 = now_ms();
+    r_A.assign(m, 0.0);
+    if (r_Ac.empty())
+      level_radii(m, dim, coords_A.data(), r_A.data(), nullptr, nullptr, nullptr, nullptr);
+    else
+      level_radii(m, dim, coords_A.data(), r_A.data(), &As[l + 1], &Ps[l + 1], coords_Ac.data(), r_Ac.data());
+    st.host_radii_ms += now_ms() - t0;
+
+    std::vector<int32_t> v_A(n);  // :605
+    for (int a = 0; a < m; ++a)
+      for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) v_A[P.indices[c]] = a;
+    // initial local coordinates in the reference's draw order (forceatlas.hpp:341, 356-358)
+    std::vector<double> init((size_t)n * dim);
+    {
+      std::mt19937 gen(resolve_seed(opt.seed));
+      std::uniform_real_distribution<double> random(-1.0, 1.0);
+      for (int a = 0; a < m; ++a)
+        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
+          for (int k = 0; k < dim; ++k) init[(size_t)P.indices[c] * dim + k] = random(gen);
+    }
+    ge_params p;
+    ge_params_default_multilevel(&p);
+    p.iterations = opt.level_iterations;  // :793
+    p.precision = opt.precision;
+    std::vector<double> coords((size_t)n * dim);
+    const double t1 = now_ms();
+    double pairs = 0.0;
+    multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(), init.data(), coords.data(),
+                     dim, p, false, &pairs);
+    st.levels_ms += now_ms() - t1;
+    st.pair_interactions += pairs * p.iterations;
+    st.edge_visits += double(A.nnz) * p.iterations;
+    return coords;
+  }
+};
+
+template <typename F>
+ge_status guarded(F&& body) {
+  try {
+    body();
+    return GE_OK;
+  } catch (const Fail& f) {
+    return f.st;
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed");
+    return GE_ERR_OOM;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return GE_ERR_INVALID;
+  }
+}
+
+void require_ctx(ge_context* ctx) {
+  GE_REQUIRE(ctx != nullptr, "context is null");
+  GE_CUDA(cudaSetDevice(ctx->device));
+}
+
+}  // namespace
+}  // namespace ge
+
+struct ge_flat_plan {
+  std::unique_ptr<ge::FlatSolver> solver;
+};
+
+using namespace ge;
+
+extern "C" {
+
+const char* ge_version(void) { return "graph-embed_b200 0.1 (sm_100a)"; }
+const char* ge_last_error(void) { return g_error.c_str(); }
+
+void ge_params_default_flat(ge_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->iterations = 100000;
+  p->ks = 0.1;
+  p->ksmax = 1.0;
+  p->repel = 1.0;
+  p->attract = 1.0;
+  p->gravity = 1.0;
+  p->delta = 1.0;
+  p->tolerate = 1.0;
+  p->use_weights = 1;
+  p->precision = GE_F64;
+}
+void ge_params_default_multilevel(ge_params* p) {
+  ge_params_default_flat(p);
+  p->iterations = 100;
+}
+void ge_embed_options_default(ge_embed_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->coarse_iterations = 100000;
+  o->level_iterations = 100;
+  o->precision = GE_F64;
+  o->verbose = 1;
+}
+
+ge_status ge_context_create(int device, void* cuda_stream, ge_context** out) {
+  return guarded([&] {
+    GE_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      set_error("no usable CUDA device (this library has no CPU fallback)");
+      throw Fail{GE_ERR_NO_DEVICE};
+    }
+    std::unique_ptr<ge_context> ctx(new ge_context);
+    if (device < 0) GE_CUDA(cudaGetDevice(&device));
+    GE_REQUIRE(device < count, "device ordinal out of range");
+    ctx->device = device;
+    GE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+      set_error("device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                "; this build contains sm_100a code only");
+      throw Fail{GE_ERR_NO_DEVICE};
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cuda_stream) {
+      ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+      GE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    *out = ctx.release();
+  });
+}
+
+void ge_context_destroy(ge_context* ctx) {
+  if (!ctx) return;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int64_t ge_context_launch_count(const ge_context* ctx) { return ctx ? ctx->launches : 0; }
+
+ge_status ge_flat_forceatlas(ge_context* ctx, const ge_csr* A, int dim, double* coords,
+                             const ge_params* p) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    GE_REQUIRE(coords != nullptr && p != nullptr, "coords / params are null");
+    flat_solve(ctx, *A, dim, coords, *p, 0);
+  });
+}
+
+ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_csr* P_T,
+                                   const int32_t* v_A, const double* coords_A, const double* r_A,
+                                   const double* init, double* coords, int dim,
+                                   const ge_params* p) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(v_A && coords_A && r_A && coords && p, "null argument");
+    std::vector<double> drawn;
+    if (init == nullptr) {  // include/forceatlas.hpp:341, 356-358
+      drawn.resize((size_t)A->rows * dim);
+      std::mt19937 gen(resolve_seed(p->seed));
+      std::uniform_real_distribution<double> random(-1.0, 1.0);
+      for (int a = 0; a < P_T->rows; ++a)
+        for (int c = P_T->indptr[a]; c < P_T->indptr[a + 1]; ++c)
+          for (int k = 0; k < dim; ++k) drawn[(size_t)P_T->indices[c] * dim + k] = random(gen);
+      init = drawn.data();
+    }
+    multilevel_solve(ctx, *A, *P_T, v_A, coords_A, r_A, init, coords, dim, *p, false, nullptr);
+  });
+}
+
+ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr* P_Ts, int dim,
+                   const ge_embed_options* opt, double* coords_out, ge_embed_stats* stats) {
+  return guarded([&] {
+    require_ctx(ctx);
+    GE_REQUIRE(n_levels >= 0 && As != nullptr && coords_out != nullptr, "null argument");
+    GE_REQUIRE(n_levels == 0 || P_Ts != nullptr, "P_Ts is null");
+    for (int l = 0; l <= n_levels; ++l) check_csr(&As[l], "As[l]");
+    for (int l = 0; l < n_levels; ++l) {  // the asserts of src/embed.cpp:564-570
+      check_csr(&P_Ts[l], "P_Ts[l]");
+      GE_REQUIRE(As[l].rows == P_Ts[l].cols, "As[l].Rows() != P_Ts[l].Cols()");
+      GE_REQUIRE(As[l + 1].rows == P_Ts[l].rows, "As[l+1].Rows() != P_Ts[l].Rows()");
+    }
+    EmbedRun run;
+    run.ctx = ctx;
+    run.L = n_levels;
+    run.dim = dim;
+    run.As = As;
+    run.Ps = P_Ts;
+    if (opt) run.opt = *opt;
+    else ge_embed_options_default(&run.opt);
+    const int64_t launches0 = ctx->launches;
+    const double h0 = ctx->h2d_bytes, d0 = ctx->d2h_bytes;
+    const double t0 = now_ms();
+    std::vector<double> r_A, coords_A;
+    std::vector<double> coords = run.level(0, r_A, coords_A);
+    std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
+    run.st.total_ms = now_ms() - t0;
+    run.st.kernel_launches = ctx->launches - launches0;
+    run.st.h2d_bytes = ctx->h2d_bytes - h0;
+    run.st.d2h_bytes = ctx->d2h_bytes - d0;
+    if (stats) *stats = run.st;
+  });
+}
+
+ge_status ge_flat_forces(ge_context* ctx, const ge_csr* A, int dim, const double* coords,
+                         const ge_params* p, int path, double* forces) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    GE_REQUIRE(coords && p && forces, "null argument");
+    if (A->rows == 0) return;
+    const bool onchip = path == 2 || (path == 0 && A->rows <= onchip_threshold());
+    if (onchip) {
+      std::vector<double> x(coords, coords + (size_t)A->rows * dim);
+      onchip_flat_solve(ctx, *A, dim, *p, x.data(), forces, true);
+      return;
+    }
+    std::unique_ptr<FlatSolver> s(make_flat_solver(ctx, *A, dim, *p, 0, A->rows));
+    s->upload_coords(coords);
+    s->launch_iteration(false);
+    s->download_forces(forces);
+  });
+}
+
+ge_status ge_multilevel_forces(ge_context* ctx, const ge_csr* A, const ge_csr* P_T,
+                               const int32_t* v_A, const double* coords_A,
+                               const double* positions, int dim, const ge_params* p,
+                               double* forces) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(v_A && coords_A && positions && p && forces, "null argument");
+    std::vector<double> r_A(std::max(P_T->rows, 1), 1.0);
+    multilevel_solve(ctx, *A, *P_T, v_A, coords_A, r_A.data(), positions, forces, dim, *p, true, nullptr);
+  });
+}
+
+ge_status ge_level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
+                         const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac) {
+  return guarded([&] {
+    GE_REQUIRE(m >= 0 && dim >= 1 && coords_A && r_A, "null argument");
+    if (P_T_c != nullptr) {
+      check_csr(A_c, "A_c");
+      check_csr(P_T_c, "P_T_c");
+      GE_REQUIRE(coords_Ac && r_Ac, "coarse centres / radii are null");
+      GE_REQUIRE(P_T_c->cols == m && A_c->rows == m, "shape mismatch");
+    }
+    level_radii(m, dim, coords_A, r_A, A_c, P_T_c, coords_Ac, r_Ac);
+  });
+}
+
+void ge_reference_uniform(uint32_t seed, int64_t count, double* out) {
+  reference_uniform(seed, count, out);
+}
+
+ge_status ge_flat_plan_create(ge_context* ctx, const ge_csr* A, int dim, const ge_params* p,
+                              int32_t row_begin, int32_t row_end, ge_flat_plan** out) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    GE_REQUIRE(p && out, "null argument");
+    std::unique_ptr<ge_flat_plan> plan(new ge_flat_plan);
+    plan->solver.reset(make_flat_solver(ctx, *A, dim, *p, row_begin, row_end));
+    *out = plan.release();
+  });
+}
+void ge_flat_plan_destroy(ge_flat_plan* plan) { delete plan; }
+int64_t ge_flat_plan_ld(const ge_flat_plan* plan) { return plan->solver->ld(); }
+int32_t ge_flat_plan_elem_size(const ge_flat_plan* plan) { return plan->solver->elem_size(); }
+ge_status ge_flat_plan_bind_coords(ge_flat_plan* plan, void* b0, void* b1) {
+  return guarded([&] {
+    GE_REQUIRE(plan && b0 && b1, "null argument");
+    plan->solver->bind_coords(b0, b1);
+  });
+}
+ge_status ge_flat_plan_upload_coords(ge_flat_plan* plan, const double* coords) {
+  return guarded([&] { plan->solver->upload_coords(coords); });
+}
+ge_status ge_flat_plan_download_coords(ge_flat_plan* plan, double* coords) {
+  return guarded([&] { plan->solver->download_coords(coords); });
+}
+ge_status ge_flat_plan_download_forces(ge_flat_plan* plan, double* forces) {
+  return guarded([&] { plan->solver->download_forces(forces); });
+}
+void* ge_flat_plan_cur_coords(ge_flat_plan* plan) { return plan->solver->cur_coords(); }
+void* ge_flat_plan_next_coords(ge_flat_plan* plan) { return plan->solver->next_coords(); }
+ge_status ge_flat_plan_launch_iteration(ge_flat_plan* plan) {
+  return guarded([&] { plan->solver->launch_iteration(true); });
+}
+void ge_flat_plan_swap(ge_flat_plan* plan) { plan->solver->swap(); }
+ge_status ge_flat_plan_iterate(ge_flat_plan* plan, int iters) {
+  return guarded([&] {
+    for (int it = 0; it < iters; ++it) {
+      plan->solver->launch_iteration(true);
+      plan->solver->swap();
+    }
+  });
+}
+ge_status ge_flat_plan_sync(ge_flat_plan* plan) {
+  return guarded([&] { GE_CUDA(cudaStreamSynchronize(plan->solver->ctx->stream)); });
+}
+void ge_flat_plan_profile(ge_flat_plan* plan, int enable) { plan->solver->profile(enable != 0); }
+ge_status ge_flat_plan_profile_get(ge_flat_plan* plan, double* repulsion_ms, int64_t* repulsion_launches,
+                                   double* attract_step_ms, int64_t* attract_step_launches) {
+  return guarded([&] {
+    plan->solver->profile_get(repulsion_ms, repulsion_launches, attract_step_ms, attract_step_launches);
+  });
+}
+
+}  // extern "C"

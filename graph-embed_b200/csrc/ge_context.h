@@ -1,0 +1,125 @@
+// graph-embed_b200 :: context, device buffers, host-side helpers shared by the .cu files.
+#ifndef GE_CONTEXT_H
+#define GE_CONTEXT_H
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "ge_common.cuh"
+
+struct ge_context {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  double h2d_bytes = 0, d2h_bytes = 0;
+};
+
+namespace ge {
+
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(
+             std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+
+// Owning device allocation (cudaMalloc / cudaFree); movable, not copyable.
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p_ = o.p_;
+      n_ = o.n_;
+      o.p_ = nullptr;
+      o.n_ = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    n_ = n;
+    if (n) GE_CUDA(cudaMalloc(&p_, n * sizeof(T)));
+  }
+  void release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    n_ = 0;
+  }
+  void zero(cudaStream_t s) {
+    if (n_) GE_CUDA(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s));
+  }
+  void upload(ge_context* ctx, const T* host, size_t n) {
+    if (n) GE_CUDA(cudaMemcpyAsync(p_, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += double(n * sizeof(T));
+  }
+  void download(ge_context* ctx, T* host, size_t n) const {
+    if (n) GE_CUDA(cudaMemcpyAsync(host, p_, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += double(n * sizeof(T));
+  }
+  T* get() const { return p_; }
+  size_t size() const { return n_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+// ---- ge_flat.cu ------------------------------------------------------------------------------
+// Type-erased device-resident flat solver (rows [row_begin,row_end) of one graph).
+class FlatSolver {
+ public:
+  virtual ~FlatSolver() {}
+  virtual int64_t ld() const = 0;
+  virtual int elem_size() const = 0;
+  virtual void bind_coords(void* b0, void* b1) = 0;
+  virtual void upload_coords(const double* aos) = 0;
+  virtual void download_coords(double* aos) = 0;
+  virtual void download_forces(double* aos) = 0;  // owned rows x dim (forces_prev)
+  virtual void* cur_coords() = 0;
+  virtual void* next_coords() = 0;
+  virtual void launch_iteration(bool update) = 0;
+  virtual void swap() = 0;
+  virtual void normalize() = 0;  // include/forceatlas.hpp:272-303 (single rank)
+  virtual void profile(bool enable) = 0;
+  virtual void profile_get(double* rep_ms, int64_t* rep_n, double* step_ms, int64_t* step_n) = 0;
+  ge_context* ctx = nullptr;
+};
+FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
+                             int row_begin, int row_end);
+
+// ---- ge_onchip.cu ----------------------------------------------------------------------------
+// Small flat solve entirely inside one CTA (coarsest level: n ~ 30-100, 100 000 iterations).
+constexpr int kOnchipMaxVertices = 1024;
+void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
+                       double* coords /* n x dim in/out */, double* forces_out /* or null */,
+                       bool forces_only);
+
+// ---- ge_multilevel.cu ------------------------------------------------------------------------
+void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
+                      const double* coords_A, const double* r_A, const double* init,
+                      double* coords_out, int dim, const ge_params& p, bool forces_only,
+                      double* pairs_out);
+
+// ---- ge_host.cpp -----------------------------------------------------------------------------
+void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
+                 const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);
+void reference_uniform(uint32_t seed, int64_t count, double* out);
+uint32_t resolve_seed(uint32_t seed);
+
+}  // namespace ge
+
+#endif  // GE_CONTEXT_H

@@ -1,0 +1,508 @@
+// graph-embed_b200 :: per-aggregate ForceAtlas + prolongation (kernel family K2), sm_100a.
+//
+// Replaces partition::forceAtlasMultilevel, /root/reference/include/forceatlas.hpp:314-574.
+// Aggregates are independent (they read only their own members and the parent level's
+// coords_A / r_A), so one level is a batch of small all-pairs problems with no global
+// synchronisation.  Work is binned by aggregate size:
+//   1 member      k_ml_singletons : closed form (centre - mean = 0  =>  x = coords_A[a]).
+//   2..32         k_onchip_warp   : one lane per member, packs of equal-size aggregates per warp.
+//   33..cta_max   k_onchip_cta    : one CTA per aggregate, positions in shared memory.
+//   larger        k_repulsion / k_attract_step over 256-aligned segments, one launch pair per
+//                 iteration, then k_ml_segment_epilogue (R-MAT hierarchies: up to ~3800 members).
+// Vertices are renumbered into SLOTS so that each aggregate is contiguous (member order of the
+// P_T row preserved, which quirk Q1 at :417 depends on).  k_ml_prep walks every CSR row once and
+// emits, per slot: the intra-aggregate degree (:362-383), the compacted intra-aggregate edge list
+// (in place, at the row's own CSR offsets) and the constant external-pull numerator
+// sum_e 100 * (cA[b]-cA[a]) / max(|cA[b]-cA[a]|, eps)  (:451-466), so that the 100 iterations touch
+// only on-chip data plus the compact edge list.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "ge_flat.cuh"
+#include "ge_onchip.cuh"
+
+namespace ge {
+
+namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+template <typename T>
+struct PrepArgs {
+  const int* I;
+  const int* J;
+  const double* Dw;        // nullptr: ones
+  const int* v_A;          // vertex -> aggregate
+  const int* vtx;          // slot -> vertex (-1: padding)
+  const int* slot_of;      // vertex -> slot
+  const int* agg_base;     // aggregate -> first slot
+  const double* cA;        // [m][D]
+  T* mass;                 // [NM][ld]
+  T* Eext;                 // [D][ld]
+  int* e_begin;
+  int* e_end;
+  int* e_idx;              // compact neighbour slots, written at the row's CSR offsets
+  T* e_w;                  // compact weights (nullptr when unweighted)
+  int64_t ld;
+  int nslots;
+  int use_weights;
+};
+
+// One warp per slot.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_ml_prep(const PrepArgs<T> a) {
+  constexpr int NM = Real<T>::kMassArrays;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= a.nslots) return;
+  const int v = a.vtx[slot];
+  if (v < 0) {  // padding slot inside a 256-aligned segment: massless, edgeless, at the origin
+    if (lane == 0) {
+      for (int k = 0; k < NM; ++k) a.mass[(int64_t)k * a.ld + slot] = (T)0;
+      for (int k = 0; k < D; ++k) a.Eext[(int64_t)k * a.ld + slot] = (T)0;
+      a.e_begin[slot] = 0;
+      a.e_end[slot] = 0;
+    }
+    return;
+  }
+  const int agg = a.v_A[v];
+  const int li = slot - a.agg_base[agg];  // local member index i of :391
+  const int rb = a.I[v], re = a.I[v + 1];
+  double ca[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) ca[k] = a.cA[(int64_t)agg * D + k];
+  double deg = 0.0, E[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) E[k] = 0.0;
+  int cnt = 0;
+  for (int e0 = rb; e0 < re; e0 += 32) {
+    const int e = e0 + lane;
+    const bool valid = e < re;
+    const int j = valid ? a.J[e] : 0;
+    const double w = (valid && a.Dw != nullptr) ? a.Dw[e] : 1.0;
+    const int b = valid ? a.v_A[j] : -1;
+    const bool same = valid && b == agg;
+    if (same) deg += a.use_weights ? w : 1.0;  // :366-369 / :376-379, self-loops included (Q5)
+    // :417 compares the GLOBAL id j with the LOCAL index i (Q1): such an edge, and a self-loop,
+    // falls through to a term that is exactly zero, so neither enters the compact list.
+    const bool internal = same && j != li && j != v;
+    if (valid && !same) {  // :451-466
+      double dir[D], d2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        dir[k] = a.cA[(int64_t)b * D + k] - ca[k];
+        d2 += dir[k] * dir[k];
+      }
+      double dis = sqrt(d2);
+      if (dis < kEpsilon) dis = kEpsilon;
+#pragma unroll
+      for (int k = 0; k < D; ++k) E[k] += dir[k] / dis * 100.0;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, internal);
+    if (internal) {
+      const int dst = rb + cnt + __popc(mask & ((1u << lane) - 1u));
+      a.e_idx[dst] = a.slot_of[j];
+      if (a.e_w) a.e_w[dst] = (T)w;
+    }
+    cnt += __popc(mask);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    deg += __shfl_xor_sync(0xffffffffu, deg, off);
+#pragma unroll
+    for (int k = 0; k < D; ++k) E[k] += __shfl_xor_sync(0xffffffffu, E[k], off);
+  }
+  if (lane == 0) {
+    const double c = deg + 1.0;
+    a.mass[slot] = (T)c;
+    if (NM > 1) a.mass[a.ld + slot] = (T)(1.5 * c);
+    if (NM > 2) a.mass[2 * a.ld + slot] = (T)(1.875 * c);
+#pragma unroll
+    for (int k = 0; k < D; ++k) a.Eext[(int64_t)k * a.ld + slot] = (T)E[k];
+    a.e_begin[slot] = rb;
+    a.e_end[slot] = rb + cnt;
+  }
+}
+
+// :539-569 for an aggregate with one member: coords - avg == 0 exactly, max -> eps, so the
+// member lands on its parent centre (r_A * 0 kept literal so a non-finite radius propagates).
+template <int D>
+__global__ void k_ml_singletons(const int* __restrict__ vtx, const int* __restrict__ v_A,
+                                const double* __restrict__ cA, const double* __restrict__ rA,
+                                int slot_begin, int count, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int v = vtx[slot_begin + t];
+  const int a = v_A[v];
+  const double c = 0.0 / kEpsilon;
+#pragma unroll
+  for (int k = 0; k < D; ++k) out[(int64_t)v * D + k] = cA[(int64_t)a * D + k] + rA[a] * c;
+}
+
+template <typename T, int D>
+__global__ void k_ml_gather_pos(const double* __restrict__ init, const int* __restrict__ vtx,
+                                int nslots, int64_t ld, T* __restrict__ pos) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int v = vtx[s];
+#pragma unroll
+  for (int k = 0; k < D; ++k) pos[(int64_t)k * ld + s] = v >= 0 ? (T)init[(int64_t)v * D + k] : (T)0;
+}
+
+template <typename T, int D>
+__global__ void k_ml_scatter_forces(const T* __restrict__ F, const int* __restrict__ vtx,
+                                    int nslots, int64_t ld, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int v = vtx[s];
+  if (v < 0) return;
+#pragma unroll
+  for (int k = 0; k < D; ++k) out[(int64_t)v * D + k] = (double)F[(int64_t)k * ld + s];
+}
+
+// :539-570 for one large aggregate whose positions live in global memory: one CTA per segment.
+template <typename T, int D>
+__global__ void __launch_bounds__(1024) k_ml_segment_epilogue(const T* __restrict__ pos, int64_t ld,
+                                                             const int4* __restrict__ segs,
+                                                             const int* __restrict__ vtx,
+                                                             const double* __restrict__ cA,
+                                                             const double* __restrict__ rA,
+                                                             double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double bc[D + 1];
+  const int4 seg = segs[blockIdx.x];
+  const int slot0 = seg.x, s = seg.y, agg = seg.z;
+  const int tid = threadIdx.x;
+  auto block_reduce = [&](double val, bool is_max) -> double {
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, val, off);
+      val = is_max ? fmax(val, o) : val + o;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid < 32) {
+      double w = (tid < (int)(blockDim.x >> 5)) ? red[tid] : 0.0;
+      for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, w, off);
+        w = is_max ? fmax(w, o) : w + o;
+      }
+      if (tid == 0) red[0] = w;
+    }
+    __syncthreads();
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  for (int k = 0; k < D; ++k) {
+    double part = 0.0;
+    for (int i = tid; i < s; i += blockDim.x) part += (double)pos[(int64_t)k * ld + slot0 + i];
+    const double tot = block_reduce(part, false);
+    if (tid == 0) bc[k] = tot / s;
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int i = tid; i < s; i += blockDim.x) {
+    double m2 = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double c = (double)pos[(int64_t)k * ld + slot0 + i] - bc[k];
+      m2 += c * c;
+    }
+    mx = fmax(mx, sqrt(m2));
+  }
+  double maxlen = block_reduce(mx, true);
+  if (maxlen < kEpsilon) maxlen = kEpsilon;
+  for (int i = tid; i < s; i += blockDim.x) {
+    const int v = vtx[slot0 + i];
+    for (int k = 0; k < D; ++k) {
+      const double c = ((double)pos[(int64_t)k * ld + slot0 + i] - bc[k]) / maxlen;
+      out[(int64_t)v * D + k] = cA[(int64_t)agg * D + k] + rA[agg] * c;
+    }
+  }
+}
+
+template <typename T>
+void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
+                  const double* coords_A, const double* r_A, const double* init,
+                  double* coords_out, int dim, const ge_params& p, bool forces_only,
+                  double* pairs_out) {
+  constexpr int NM = Real<T>::kMassArrays;
+  const int n = A.rows, m = P.rows;
+  const int nnz = A.indptr[n];
+  const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
+  const bool weighted = p.use_weights && A.data != nullptr;
+
+  // ---- host: bin aggregates by size and lay out the slots -------------------------------------
+  std::vector<int> by_size[33];
+  std::vector<int> cta_aggs, grid_aggs;
+  double pairs = 0.0;
+  for (int a = 0; a < m; ++a) {
+    const int s = P.indptr[a + 1] - P.indptr[a];
+    pairs += double(s) * double(s - 1);
+    if (s <= 0) continue;
+    if (s <= 32) by_size[s].push_back(a);
+    else if (s <= cta_max) cta_aggs.push_back(a);
+    else grid_aggs.push_back(a);
+  }
+  if (pairs_out) *pairs_out = pairs;
+  auto size_of = [&](int a) { return P.indptr[a + 1] - P.indptr[a]; };
+  std::sort(cta_aggs.begin(), cta_aggs.end(), [&](int x, int y) { return size_of(x) > size_of(y); });
+
+  std::vector<int> agg_base(std::max(m, 1), 0);
+  std::vector<int4> segs, cta_tasks, packs;
+  int64_t cursor = 0;
+  for (int a : grid_aggs) {
+    const int s = size_of(a);
+    agg_base[a] = (int)cursor;
+    segs.push_back(make_int4((int)cursor, s, a, 0));
+    cursor = round_up(cursor + s, kTileJ);
+  }
+  const int grid_slots = (int)cursor;
+  int cta_threads = 32, cta_size_max = 1;
+  for (int a : cta_aggs) {
+    const int s = size_of(a);
+    agg_base[a] = (int)cursor;
+    int L = 1;
+    while (L < 32 && (int64_t)s * (L * 2) <= 1024) L *= 2;
+    cta_tasks.push_back(make_int4((int)cursor, s, a, L));
+    cta_threads = std::max<int>(cta_threads, (int)round_up((int64_t)s * L, 32));
+    cta_size_max = std::max(cta_size_max, s);
+    cursor += s;
+  }
+  const int single_lo = forces_only ? 1 : 2;  // forces hook: singletons go through the warp tier
+  for (int s = 32; s >= single_lo; --s) {
+    const int per = 32 / s;
+    const auto& list = by_size[s];
+    for (size_t i0 = 0; i0 < list.size(); i0 += per) {
+      const int cnt = (int)std::min<size_t>(per, list.size() - i0);
+      packs.push_back(make_int4((int)cursor, s, cnt, 0));
+      for (int q = 0; q < cnt; ++q) {
+        agg_base[list[i0 + q]] = (int)cursor;
+        cursor += s;
+      }
+    }
+  }
+  const int single_begin = (int)cursor;
+  int n_single = 0;
+  if (!forces_only) {
+    for (int a : by_size[1]) agg_base[a] = (int)cursor++;
+    n_single = (int)by_size[1].size();
+  }
+  const int nslots = (int)cursor;
+  const int64_t ld = round_up(std::max(nslots, 1), kTileJ);
+  std::vector<int> vtx((size_t)ld, -1), slot_of(std::max(n, 1), -1), agg_of_slot((size_t)ld, -1);
+  for (int a = 0; a < m; ++a) {
+    const int s = size_of(a);
+    for (int i = 0; i < s; ++i) {
+      const int v = P.indices[P.indptr[a] + i];
+      vtx[agg_base[a] + i] = v;
+      slot_of[v] = agg_base[a] + i;
+      agg_of_slot[agg_base[a] + i] = a;
+    }
+  }
+
+  // ---- upload ------------------------------------------------------------------------------
+  DevBuf<int> d_I(n + 1), d_J(std::max(nnz, 1)), d_vA(std::max(n, 1)), d_vtx((size_t)ld),
+      d_slot_of(std::max(n, 1)), d_agg_base(std::max(m, 1)), d_agg_of_slot((size_t)ld),
+      d_eb((size_t)ld), d_ee((size_t)ld), d_eidx(std::max(nnz, 1));
+  DevBuf<double> d_Dw, d_cA((size_t)std::max(m, 1) * dim), d_rA(std::max(m, 1)),
+      d_init((size_t)std::max(n, 1) * dim), d_out((size_t)std::max(n, 1) * dim);
+  DevBuf<T> d_mass((size_t)NM * ld), d_E((size_t)dim * ld), d_ew;
+  d_I.upload(ctx, A.indptr, n + 1);
+  d_J.upload(ctx, A.indices, nnz);
+  if (A.data != nullptr) {
+    d_Dw.alloc(std::max(nnz, 1));
+    d_Dw.upload(ctx, A.data, nnz);
+  }
+  if (weighted) d_ew.alloc(std::max(nnz, 1));
+  d_vA.upload(ctx, v_A, n);
+  d_vtx.upload(ctx, vtx.data(), (size_t)ld);
+  d_slot_of.upload(ctx, slot_of.data(), n);
+  d_agg_base.upload(ctx, agg_base.data(), m);
+  d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
+  d_cA.upload(ctx, coords_A, (size_t)m * dim);
+  d_rA.upload(ctx, r_A, m);
+  d_init.upload(ctx, init, (size_t)n * dim);
+  d_eb.zero(ctx->stream);
+  d_ee.zero(ctx->stream);
+
+  // ---- prep --------------------------------------------------------------------------------
+  PrepArgs<T> pa;
+  pa.I = d_I.get();
+  pa.J = d_J.get();
+  pa.Dw = A.data != nullptr ? d_Dw.get() : nullptr;
+  pa.v_A = d_vA.get();
+  pa.vtx = d_vtx.get();
+  pa.slot_of = d_slot_of.get();
+  pa.agg_base = d_agg_base.get();
+  pa.cA = d_cA.get();
+  pa.mass = d_mass.get();
+  pa.Eext = d_E.get();
+  pa.e_begin = d_eb.get();
+  pa.e_end = d_ee.get();
+  pa.e_idx = d_eidx.get();
+  pa.e_w = weighted ? d_ew.get() : nullptr;
+  pa.ld = ld;
+  pa.nslots = nslots;
+  pa.use_weights = p.use_weights;
+  d_mass.zero(ctx->stream);
+  d_E.zero(ctx->stream);
+  if (nslots > 0) {
+    const unsigned grid = (unsigned)(((int64_t)nslots * 32 + 255) / 256);
+    if (dim == 2) k_ml_prep<T, 2><<<grid, 256, 0, ctx->stream>>>(pa);
+    else k_ml_prep<T, 3><<<grid, 256, 0, ctx->stream>>>(pa);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  OnchipArgs<T> oa;
+  oa.init_aos = d_init.get();
+  oa.vtx = d_vtx.get();
+  oa.agg_of_slot = d_agg_of_slot.get();
+  oa.mass = d_mass.get();
+  oa.e_begin = d_eb.get();
+  oa.e_end = d_ee.get();
+  oa.e_idx = d_eidx.get();
+  oa.e_w = weighted ? d_ew.get() : nullptr;
+  oa.Eext = d_E.get();
+  oa.ld = ld;
+  oa.cA_aos = d_cA.get();
+  oa.rA = d_rA.get();
+  oa.out_aos = d_out.get();
+  oa.iters = p.iterations;
+  oa.forces_only = forces_only ? 1 : 0;
+  oa.normalize = 0;
+  oa.ph = make_physics<T>(p);
+
+  // ---- singletons --------------------------------------------------------------------------
+  if (n_single > 0) {
+    const unsigned grid = (unsigned)((n_single + 255) / 256);
+    if (dim == 2)
+      k_ml_singletons<2><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), d_cA.get(),
+                                                        d_rA.get(), single_begin, n_single, d_out.get());
+    else
+      k_ml_singletons<3><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), d_cA.get(),
+                                                        d_rA.get(), single_begin, n_single, d_out.get());
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  // ---- warp tier ---------------------------------------------------------------------------
+  DevBuf<int4> d_packs(std::max<size_t>(packs.size(), 1)), d_tasks(std::max<size_t>(cta_tasks.size(), 1)),
+      d_segs(std::max<size_t>(segs.size(), 1));
+  if (!packs.empty()) {
+    d_packs.upload(ctx, packs.data(), packs.size());
+    OnchipArgs<T> wa = oa;
+    wa.tasks = d_packs.get();
+    launch_onchip_warp<T>(ctx, wa, (int)packs.size(), dim);
+  }
+  // ---- CTA tier ----------------------------------------------------------------------------
+  if (!cta_tasks.empty()) {
+    d_tasks.upload(ctx, cta_tasks.data(), cta_tasks.size());
+    OnchipArgs<T> ca = oa;
+    ca.tasks = d_tasks.get();
+    launch_onchip_cta<T>(ctx, ca, (int)cta_tasks.size(), dim, true, cta_threads, cta_size_max);
+  }
+  // ---- grid tier ---------------------------------------------------------------------------
+  DevBuf<T> d_pos0, d_pos1, d_Frep, d_Fprev;
+  DevBuf<BlockDesc> d_blocks;
+  if (!segs.empty()) {
+    d_segs.upload(ctx, segs.data(), segs.size());
+    d_pos0.alloc((size_t)dim * ld);
+    d_pos1.alloc((size_t)dim * ld);
+    d_Frep.alloc((size_t)dim * ld);
+    d_Fprev.alloc((size_t)dim * ld);
+    d_pos0.zero(ctx->stream);
+    d_pos1.zero(ctx->stream);
+    d_Frep.zero(ctx->stream);
+    d_Fprev.zero(ctx->stream);
+    const unsigned ggrid = (unsigned)((grid_slots + 255) / 256);
+    if (dim == 2) k_ml_gather_pos<T, 2><<<ggrid, 256, 0, ctx->stream>>>(d_init.get(), d_vtx.get(), grid_slots, ld, d_pos0.get());
+    else k_ml_gather_pos<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_init.get(), d_vtx.get(), grid_slots, ld, d_pos0.get());
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+    // row blocks: 128 threads x IPT rows, each against its own segment's 256-aligned column range
+    const int rep_threads = 128;
+    int64_t total_rows = 0;
+    for (auto& sg : segs) total_rows += sg.y;
+    const int ipt = total_rows >= (int64_t)ctx->sm_count * 2 * rep_threads * 2 ? 2 : 1;
+    std::vector<BlockDesc> blocks;
+    for (auto& sg : segs) {
+      const int j0 = sg.x, j1 = (int)round_up((int64_t)sg.x + sg.y, kTileJ);
+      for (int r = sg.x; r < sg.x + sg.y; r += rep_threads * ipt)
+        blocks.push_back(BlockDesc{r, std::min(sg.x + sg.y, r + rep_threads * ipt), j0, j1});
+    }
+    d_blocks.alloc(blocks.size());
+    d_blocks.upload(ctx, blocks.data(), blocks.size());
+    T* pos[2] = {d_pos0.get(), d_pos1.get()};
+    int cur = 0;
+    const int iters = forces_only ? 1 : p.iterations;
+    const double avg_deg = grid_slots > 0 ? double(nnz) / std::max(n, 1) : 0.0;
+    for (int it = 0; it < iters; ++it) {
+      RepArgs<T> ra;
+      ra.pos = pos[cur];
+      ra.mass = d_mass.get();
+      ra.F = d_Frep.get();
+      ra.blocks = d_blocks.get();
+      ra.ld = ld;
+      ra.ldf = ld;
+      ra.f_row_base = 0;
+      ra.repel = oa.ph.repel;
+      ra.eps2 = oa.ph.eps2;
+      launch_repulsion<T>(ctx, ra, (int)blocks.size(), rep_threads, ipt, dim);
+      StepArgs<T> sa;
+      sa.e_begin = d_eb.get();
+      sa.e_end = d_ee.get();
+      sa.J = d_eidx.get();
+      sa.W = weighted ? d_ew.get() : nullptr;
+      sa.pos_cur = pos[cur];
+      sa.pos_next = pos[cur ^ 1];
+      sa.Frep = d_Frep.get();
+      sa.Fprev = d_Fprev.get();
+      sa.mass = d_mass.get();
+      sa.Eext = d_E.get();
+      sa.ld = ld;
+      sa.ldf = ld;
+      sa.row0 = 0;
+      sa.nrows = grid_slots;
+      sa.update = forces_only ? 0 : 1;
+      sa.ph = oa.ph;
+      launch_attract_step<T>(ctx, sa, dim, group_for_degree(avg_deg), true);
+      if (!forces_only) cur ^= 1;
+    }
+    if (forces_only) {
+      if (dim == 2) k_ml_scatter_forces<T, 2><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
+      else k_ml_scatter_forces<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
+    } else {
+      if (dim == 2) k_ml_segment_epilogue<T, 2><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), d_cA.get(), d_rA.get(), d_out.get());
+      else k_ml_segment_epilogue<T, 3><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), d_cA.get(), d_rA.get(), d_out.get());
+    }
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+
+  d_out.download(ctx, coords_out, (size_t)n * dim);
+  GE_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
+                      const double* coords_A, const double* r_A, const double* init,
+                      double* coords_out, int dim, const ge_params& p, bool forces_only,
+                      double* pairs_out) {
+  GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+  GE_REQUIRE(A.rows == A.cols, "A must be square");
+  GE_REQUIRE(P_T.cols == A.rows, "P_T.cols must equal A.rows");
+  GE_REQUIRE(P_T.indptr[P_T.rows] == A.rows, "P_T must list every vertex exactly once");
+  if (p.precision == GE_F32)
+    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out);
+  else
+    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out);
+}
+
+}  // namespace ge

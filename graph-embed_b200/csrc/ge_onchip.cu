@@ -1,0 +1,409 @@
+// graph-embed_b200 :: on-chip persistent ForceAtlas solvers (kernel families K3 and K2), sm_100a.
+//
+// k_onchip_cta   All iterations of one small all-pairs problem inside ONE CTA: positions and
+//                masses live in shared memory (double-buffered: one __syncthreads per iteration),
+//                L lanes share one vertex's pair loop and combine with warp shuffles, the per-vertex
+//                state (x, previous force, mass) stays in registers.  Zero launches and zero global
+//                synchronisation per iteration.  Used for
+//                  * the coarsest level: partition::forceAtlas with its default 100 000 iterations on
+//                    n ~ 30-100 vertices (/root/reference/include/forceatlas.hpp:146-270, called
+//                    from src/embed.cpp:586), which dominates embed() wall time, and
+//                  * aggregates of 33..1024 members in forceAtlasMultilevel (:390-538) followed by
+//                    the centre / max-normalise / prolongation epilogue (:539-570).
+// k_onchip_warp  The same for aggregates of 2..32 members: one lane per member, several
+//                equal-size aggregates packed into one warp, __syncwarp instead of __syncthreads.
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "ge_onchip.cuh"
+
+namespace ge {
+
+namespace {
+
+template <typename T, int D, bool ML>
+__global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
+  constexpr int NM = Real<T>::kMassArrays;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  __shared__ double bc[D + 1];
+
+  const int4 task = a.tasks[blockIdx.x];
+  const int slot0 = task.x, s = task.y, agg = task.z, L = task.w;
+  const int S = (s + 1) & ~1;
+  T* pos = reinterpret_cast<T*>(smem_raw);  // [2][D][S]
+  T* ms = pos + 2 * D * S;                  // [NM][S]
+
+  const int tid = threadIdx.x;
+  const int lshift = 31 - __clz(L);
+  const int lv = tid >> lshift;
+  const int part = tid & (L - 1);
+  const bool owner = lv < s;
+  const int slot = slot0 + (owner ? lv : 0);
+  const int v = a.vtx ? a.vtx[slot] : slot;
+
+  T x[D], fprev[D], E[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    x[k] = (T)a.init_aos[(int64_t)v * D + k];
+    fprev[k] = (T)0;
+    E[k] = (ML && a.Eext) ? a.Eext[(int64_t)k * a.ld + slot] : (T)0;
+  }
+  const T ci = a.mass[slot];
+  const T ci_repel = ci * a.ph.repel;
+  const int eb = owner ? a.e_begin[slot] : 0;
+  const int ee = owner ? a.e_end[slot] : 0;
+  if (owner && part == 0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) pos[k * S + lv] = x[k];
+    ms[lv] = ci;
+    if (NM > 1) ms[S + lv] = (T)1.5 * ci;
+    if (NM > 2) ms[2 * S + lv] = (T)1.875 * ci;
+  }
+  __syncthreads();
+
+  int cur = 0;
+  const int iters = a.forces_only ? 1 : a.iters;
+  for (int it = 0; it < iters; ++it) {
+    const T* pc = pos + cur * D * S;
+    T f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = (T)0;
+    if (owner) {
+#pragma unroll 2
+      for (int j = part; j < s; j += L) {
+        T xj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xj[k] = pc[k * S + j];
+        pair_accumulate<T, D>(x, xj, ms[j], ms[(NM > 1 ? 1 : 0) * S + j],
+                              ms[(NM > 2 ? 2 : 0) * S + j], a.ph.eps2, f);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+      for (int e = eb + part; e < ee; e += L) {
+        const int j = a.e_idx[e] - slot0;
+        const T w = (a.e_w != nullptr && a.ph.use_weights) ? a.e_w[e] : (T)1;
+        T d[D];
+        T r2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          d[k] = pc[k * S + j] - x[k];
+          r2 = fma(d[k], d[k], r2);
+        }
+        const T g = attraction_factor<T>(r2, w, ci, a.ph);
+#pragma unroll
+        for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+      }
+    }
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
+    }
+    vertex_step<T, D, ML>(x, f, fprev, E, ci, a.ph);
+    if (a.forces_only) break;
+    if (owner && part == 0) {
+      T* pn = pos + (cur ^ 1) * D * S;
+#pragma unroll
+      for (int k = 0; k < D; ++k) pn[k * S + lv] = x[k];
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+
+  if (a.forces_only) {
+    if (owner && part == 0) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.out_aos[(int64_t)v * D + k] = (double)fprev[k];
+    }
+    return;
+  }
+  if (!ML && !a.normalize) {
+    if (owner && part == 0) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.out_aos[(int64_t)v * D + k] = (double)x[k];
+    }
+    return;
+  }
+
+  // Epilogue: subtract the mean, divide by the largest norm (:272-303 flat / :539-564 multilevel),
+  // and for the multilevel kernel map into the parent ball (:565-569).
+  const T* pc = pos + cur * D * S;
+  auto block_reduce = [&](double val, bool is_max) -> double {
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, val, off);
+      val = is_max ? fmax(val, o) : val + o;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid < 32) {
+      double w = (tid < (int)((blockDim.x + 31) >> 5)) ? red[tid] : 0.0;
+      for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, w, off);
+        w = is_max ? fmax(w, o) : w + o;
+      }
+      if (tid == 0) red[0] = w;
+    }
+    __syncthreads();
+    const double out = red[0];
+    __syncthreads();
+    return out;
+  };
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double part_sum = 0.0;
+    for (int i = tid; i < s; i += blockDim.x) part_sum += (double)pc[k * S + i];
+    const double tot = block_reduce(part_sum, false);
+    if (tid == 0) bc[k] = tot / s;
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int i = tid; i < s; i += blockDim.x) {
+    double m2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = (double)pc[k * S + i] - bc[k];
+      m2 += c * c;
+    }
+    mx = fmax(mx, sqrt(m2));
+  }
+  double maxlen = block_reduce(mx, true);
+  if (ML && maxlen < kEpsilon) maxlen = kEpsilon;
+  for (int i = tid; i < s; i += blockDim.x) {
+    const int vi = a.vtx ? a.vtx[slot0 + i] : slot0 + i;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = ((double)pc[k * S + i] - bc[k]) / maxlen;
+      a.out_aos[(int64_t)vi * D + k] =
+          ML ? a.cA_aos[(int64_t)agg * D + k] + a.rA[agg] * c : c;
+    }
+  }
+}
+
+constexpr int kWarpsPerCta = 8;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_onchip_warp(const OnchipArgs<T> a,
+                                                                   int npacks) {
+  constexpr int NM = Real<T>::kMassArrays;
+  __shared__ T pos_s[kWarpsPerCta][2][D][32];
+  __shared__ T ms_s[kWarpsPerCta][NM][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * kWarpsPerCta + warp;
+  if (wid >= npacks) return;
+  const int4 pack = a.tasks[wid];
+  const int slot0 = pack.x, s = pack.y, count = pack.z;
+  const bool active = lane < s * count;
+  const int g = active ? lane / s : 0;
+  const int base = g * s;
+  const int slot = slot0 + (active ? lane : 0);
+  const int v = a.vtx ? a.vtx[slot] : slot;
+
+  T x[D], fprev[D], E[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    x[k] = (T)a.init_aos[(int64_t)v * D + k];
+    fprev[k] = (T)0;
+    E[k] = a.Eext ? a.Eext[(int64_t)k * a.ld + slot] : (T)0;
+  }
+  const T ci = a.mass[slot];
+  const T ci_repel = ci * a.ph.repel;
+  const int eb = active ? a.e_begin[slot] : 0;
+  const int ee = active ? a.e_end[slot] : 0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) pos_s[warp][0][k][lane] = x[k];
+  ms_s[warp][0][lane] = ci;
+  if (NM > 1) ms_s[warp][NM > 1 ? 1 : 0][lane] = (T)1.5 * ci;
+  if (NM > 2) ms_s[warp][NM > 2 ? 2 : 0][lane] = (T)1.875 * ci;
+  __syncwarp();
+
+  int cur = 0;
+  const int iters = a.forces_only ? 1 : a.iters;
+  for (int it = 0; it < iters; ++it) {
+    T f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = (T)0;
+    if (active) {
+      for (int j = base; j < base + s; ++j) {  // the self pair contributes exactly 0 (Q4)
+        T xj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xj[k] = pos_s[warp][cur][k][j];
+        pair_accumulate<T, D>(x, xj, ms_s[warp][0][j], ms_s[warp][NM > 1 ? 1 : 0][j],
+                              ms_s[warp][NM > 2 ? 2 : 0][j], a.ph.eps2, f);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+      for (int e = eb; e < ee; ++e) {
+        const int j = a.e_idx[e] - slot0;
+        const T w = (a.e_w != nullptr && a.ph.use_weights) ? a.e_w[e] : (T)1;
+        T d[D];
+        T r2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          d[k] = pos_s[warp][cur][k][j] - x[k];
+          r2 = fma(d[k], d[k], r2);
+        }
+        const T gf = attraction_factor<T>(r2, w, ci, a.ph);
+#pragma unroll
+        for (int k = 0; k < D; ++k) f[k] = fma(d[k], gf, f[k]);
+      }
+    }
+    vertex_step<T, D, true>(x, f, fprev, E, ci, a.ph);
+    if (a.forces_only) break;
+#pragma unroll
+    for (int k = 0; k < D; ++k) pos_s[warp][cur ^ 1][k][lane] = x[k];
+    cur ^= 1;
+    __syncwarp();
+  }
+
+  if (!active) return;
+  if (a.forces_only) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) a.out_aos[(int64_t)v * D + k] = (double)fprev[k];
+    return;
+  }
+  // :539-570, member order ascending exactly like the reference's serial loops.
+  double avg[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double sum = 0.0;
+    for (int j = base; j < base + s; ++j) sum += (double)pos_s[warp][cur][k][j];
+    avg[k] = sum / s;
+  }
+  double maxlen = 0.0;
+  for (int j = base; j < base + s; ++j) {
+    double m2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = (double)pos_s[warp][cur][k][j] - avg[k];
+      m2 += c * c;
+    }
+    maxlen = fmax(maxlen, sqrt(m2));
+  }
+  if (maxlen < kEpsilon) maxlen = kEpsilon;
+  const int agg = a.agg_of_slot[slot];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double c = ((double)x[k] - avg[k]) / maxlen;
+    a.out_aos[(int64_t)v * D + k] = a.cA_aos[(int64_t)agg * D + k] + a.rA[agg] * c;
+  }
+}
+
+template <typename T>
+size_t cta_smem(int dim, int max_size) {
+  const int S = (max_size + 1) & ~1;
+  return (size_t)(2 * dim + Real<T>::kMassArrays) * S * sizeof(T);
+}
+
+}  // namespace
+
+template <typename T>
+void launch_onchip_cta(ge_context* ctx, const OnchipArgs<T>& a, int ntasks, int dim, bool ml,
+                       int threads, int max_size) {
+  if (ntasks == 0) return;
+  const size_t smem = cta_smem<T>(dim, max_size);
+  const void* fn = dim == 2 ? (ml ? (const void*)k_onchip_cta<T, 2, true> : (const void*)k_onchip_cta<T, 2, false>)
+                            : (ml ? (const void*)k_onchip_cta<T, 3, true> : (const void*)k_onchip_cta<T, 3, false>);
+  if (smem > 48 * 1024)
+    GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&a};
+  GE_CUDA(cudaLaunchKernel(fn, dim3(ntasks), dim3(threads), args, smem, ctx->stream));
+  ctx->launches++;
+}
+
+template <typename T>
+void launch_onchip_warp(ge_context* ctx, const OnchipArgs<T>& a, int npacks, int dim) {
+  if (npacks == 0) return;
+  const int ctas = (npacks + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (dim == 2)
+    k_onchip_warp<T, 2><<<ctas, kWarpsPerCta * 32, 0, ctx->stream>>>(a, npacks);
+  else
+    k_onchip_warp<T, 3><<<ctas, kWarpsPerCta * 32, 0, ctx->stream>>>(a, npacks);
+  GE_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+template void launch_onchip_cta<double>(ge_context*, const OnchipArgs<double>&, int, int, bool, int, int);
+template void launch_onchip_cta<float>(ge_context*, const OnchipArgs<float>&, int, int, bool, int, int);
+template void launch_onchip_warp<double>(ge_context*, const OnchipArgs<double>&, int, int);
+template void launch_onchip_warp<float>(ge_context*, const OnchipArgs<float>&, int, int);
+
+// ---------------------------------------------------------------------------------------------
+// Coarsest-level flat solve: the whole graph is one task of k_onchip_cta.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// Lanes per vertex: the largest power of two (<= 32) such that n * L threads fit in one CTA.
+int lanes_for(int n, int max_threads) {
+  int L = 1;
+  while (L < 32 && (int64_t)n * (L * 2) <= max_threads) L *= 2;
+  return L;
+}
+
+template <typename T>
+void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p, double* coords,
+                   double* forces_out, bool forces_only) {
+  const int n = A.rows;
+  const int nnz = A.indptr[n];
+  const bool weighted = p.use_weights && A.data != nullptr;
+  std::vector<T> mass(n), w;
+  for (int i = 0; i < n; ++i) {  // include/forceatlas.hpp:127-140
+    double s = 0.0;
+    if (weighted) {
+      for (int e = A.indptr[i]; e < A.indptr[i + 1]; ++e) s += A.data[e];
+    } else {
+      s = 1.0 * (A.indptr[i + 1] - A.indptr[i]);
+    }
+    mass[i] = (T)(s + 1.0);
+  }
+  DevBuf<T> d_mass(n), d_w;
+  DevBuf<int> d_I(n + 1), d_J(std::max(nnz, 1));
+  DevBuf<double> d_init((size_t)n * dim), d_out((size_t)n * dim);
+  DevBuf<int4> d_task(1);
+  d_mass.upload(ctx, mass.data(), n);
+  d_I.upload(ctx, A.indptr, n + 1);
+  d_J.upload(ctx, A.indices, nnz);
+  if (weighted) {
+    w.resize(nnz);
+    for (int e = 0; e < nnz; ++e) w[e] = (T)A.data[e];
+    d_w.alloc(std::max(nnz, 1));
+    d_w.upload(ctx, w.data(), nnz);
+  }
+  d_init.upload(ctx, coords, (size_t)n * dim);
+  const int L = lanes_for(n, 1024);
+  const int threads = (int)round_up((int64_t)n * L, 32);
+  const int4 task = make_int4(0, n, 0, L);
+  d_task.upload(ctx, &task, 1);
+
+  OnchipArgs<T> a;
+  a.init_aos = d_init.get();
+  a.mass = d_mass.get();
+  a.e_begin = d_I.get();
+  a.e_end = d_I.get() + 1;
+  a.e_idx = d_J.get();
+  a.e_w = weighted ? d_w.get() : nullptr;
+  a.ld = n;
+  a.tasks = d_task.get();
+  a.out_aos = d_out.get();
+  a.iters = p.iterations;
+  a.forces_only = forces_only ? 1 : 0;
+  a.normalize = p.normalize;
+  a.ph = make_physics<T>(p);
+  launch_onchip_cta<T>(ctx, a, 1, dim, false, threads, n);
+  d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);
+  GE_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
+                       double* coords, double* forces_out, bool forces_only) {
+  GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+  GE_REQUIRE(A.rows >= 1 && A.rows <= kOnchipMaxVertices, "on-chip flat solve needs 1..1024 vertices");
+  if (p.precision == GE_F32)
+    onchip_flat_t<float>(ctx, A, dim, p, coords, forces_out, forces_only);
+  else
+    onchip_flat_t<double>(ctx, A, dim, p, coords, forces_out, forces_only);
+}
+
+}  // namespace ge

@@ -1,0 +1,52 @@
+"""Shared test helpers: golden loaders and tolerance metrics."""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Tolerances stated by BASELINE.json's north_star for per-iteration force vectors.
+TOL_F64 = 1e-10
+TOL_F32 = 1e-4
+
+
+def load_flat_golden():
+    z = np.load(os.path.join(GOLDEN, "flat_grid12.npz"))
+    n = len(z["indptr"]) - 1
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    return A, z
+
+
+def load_hier_golden():
+    z = np.load(os.path.join(GOLDEN, "hier_grid30.npz"))
+    L = int(z["L"])
+    As, Ps = [], []
+    for l in range(L + 1):
+        n = len(z["A%d_indptr" % l]) - 1
+        As.append(sp.csr_matrix((z["A%d_data" % l], z["A%d_indices" % l], z["A%d_indptr" % l]), shape=(n, n)))
+    for l in range(L):
+        m = len(z["P%d_indptr" % l]) - 1
+        idx = z["P%d_indices" % l]
+        Ps.append(sp.csr_matrix((np.ones(len(idx)), idx, z["P%d_indptr" % l]), shape=(m, As[l].shape[0])))
+    return As, Ps, z
+
+
+def force_error(F, F_ref, scale):
+    """Per-vertex |F - F_ref|_2 divided by the conditioning scale the oracle reports (the sum of
+    the norms of the individual terms that were added into that vertex's force)."""
+    return np.linalg.norm(F - F_ref, axis=1) / np.maximum(scale, 1e-300)
+
+
+def layout_stats(A, x):
+    """Edge-length mean / coefficient of variation and a sampled normalised stress."""
+    coo = A.tocoo()
+    keep = coo.row < coo.col
+    el = np.linalg.norm(x[coo.row[keep]] - x[coo.col[keep]], axis=1)
+    rng = np.random.default_rng(0)
+    n = A.shape[0]
+    i, j = rng.integers(0, n, 4000), rng.integers(0, n, 4000)
+    dist = np.linalg.norm(x[i] - x[j], axis=1)
+    extent = np.linalg.norm(x - x.mean(0), axis=1).max()
+    return dict(edge_mean=el.mean() / extent, edge_cv=el.std() / el.mean(),
+                pair_mean=dist.mean() / extent)

@@ -1,0 +1,87 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares,
+refuses to compute without a device, and its host-side level-driver step matches the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import load_hier_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol(capi):
+    header = open(os.path.join(ROOT, "include", "graph_embed_b200.h")).read()
+    declared = set(re.findall(r"\b(ge_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = capi.lib()
+    for name in sorted(declared):
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.ge_version()
+
+
+def test_defaults_match_reference(capi):
+    """include/forceatlas.hpp:92-103 and :320-331 (iterations = 100 as src/embed.cpp:793 passes)."""
+    p = capi.flat_params()
+    assert (p.iterations, p.ks, p.ksmax, p.repel, p.attract, p.gravity, p.delta, p.tolerate) == \
+        (100000, 0.1, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
+    assert (p.use_weights, p.linlog, p.nohubs, p.normalize, p.precision) == (1, 0, 0, 0, capi.GE_F64)
+    assert capi.multilevel_params().iterations == 100
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.GeError) as e:
+        capi.Context(0)
+    assert e.value.status == capi.GE_ERR_NO_DEVICE
+
+
+def test_reference_uniform_matches_oracle(capi, oracle):
+    assert np.array_equal(capi.reference_uniform(99, 1001), oracle.mt_uniform(99, 1001))
+
+
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_level_radii_matches_golden(capi, L):
+    """ge_level_radii (heap-based) against the reference's sort-based ball growing, bit for bit."""
+    As, Ps, z = load_hier_golden()
+    AsL, PsL = As[-(L + 1):], Ps[-L:]
+    pre = "radii_L%d_" % L
+    if L == 1:
+        cA, rA = capi.level_radii(z[pre + "coords_A_in"], 2)
+    else:
+        cA, rA = capi.level_radii(z[pre + "coords_A_in"], 2, AsL[1], PsL[1], z[pre + "coords_Ac"], z[pre + "r_Ac"])
+    assert np.array_equal(cA, z[pre + "coords_A_out"])
+    assert np.array_equal(rA, z[pre + "r_A_out"])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_level_radii_matches_oracle_random(capi, oracle, graphs, dim):
+    A = graphs.rgg(1500, 9.0, seed=9)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=30)
+    rng = np.random.default_rng(4)
+    # base case on the coarsest level
+    m = As[-1].shape[0]
+    x = rng.normal(size=(m, dim))
+    c1, r1 = capi.level_radii(x, dim)
+    c2, r2 = oracle.radii(x, dim)
+    assert np.array_equal(c1, c2) and np.array_equal(r1, r2)
+    # general case one level up, including duplicate points (zero distances) and singletons
+    l = len(Ps) - 1
+    m = As[l].shape[0]
+    x = rng.normal(size=(m, dim))
+    x[3] = x[4]
+    cAc, rAc = rng.normal(size=(Ps[l].shape[0], dim)), rng.random(Ps[l].shape[0]) + 0.1
+    c1, r1 = capi.level_radii(x, dim, As[l], Ps[l], cAc, rAc)
+    c2, r2 = oracle.radii(x, dim, As[l], Ps[l], cAc, rAc)
+    assert np.array_equal(c1, c2) and np.array_equal(r1, r2)
+
+
+def test_invalid_arguments(capi):
+    with pytest.raises(capi.GeError) as e:
+        capi.level_radii(np.zeros((3, 2)), 2, A_c=__import__("scipy.sparse").sparse.identity(4, format="csr"),
+                         P_T_c=__import__("scipy.sparse").sparse.identity(4, format="csr"),
+                         coords_Ac=np.zeros((4, 2)), r_Ac=np.ones(4))
+    assert e.value.status == capi.GE_ERR_INVALID

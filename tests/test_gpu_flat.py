@@ -1,0 +1,154 @@
+"""GPU parity of the flat ForceAtlas kernels (K1 tiled multi-CTA path, K3 on-chip path) against
+the oracle, through the C ABI.  Force tolerances are the ones BASELINE.json states: 1e-10 (FP64)
+and 1e-4 (FP32), relative to the conditioning scale of each vertex's force sum."""
+import numpy as np
+import pytest
+
+from helpers import TOL_F32, TOL_F64, force_error, load_flat_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(graphs, name):
+    if name == "grid12":
+        return load_flat_golden()[0]
+    if name == "rgg2000":
+        return graphs.rgg(2000, 10.0, seed=1)
+    if name == "galerkin":  # weighted, with self-loops (quirk Q5)
+        A = graphs.rgg(3000, 10.0, seed=2)
+        As, _ = graphs.coarsen(A, 0.25, min_coarse=200, max_levels=1)
+        return As[1]
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["grid12", "rgg2000", "galerkin"])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("path", [1, 2])
+def test_forces_fp64(ctx, capi, oracle, graphs, name, dim, path):
+    A = _graph(graphs, name)
+    n = A.shape[0]
+    if path == 2 and n > 1024:
+        pytest.skip("on-chip path holds at most 1024 vertices")
+    x0 = capi.reference_uniform(17, n * dim).reshape(n, dim)
+    F_ref, S = oracle.flat_forces(A, dim, x0)
+    F = ctx.flat_forces(A, dim, x0, capi.flat_params(), path=path)
+    err = force_error(F, F_ref, S)
+    assert err.max() < TOL_F64, err.max()
+    # plain relative error of the whole force field as well
+    assert np.linalg.norm(F - F_ref) / np.linalg.norm(F_ref) < TOL_F64
+
+
+@pytest.mark.parametrize("name", ["grid12", "rgg2000"])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("path", [1, 2])
+def test_forces_fp32(ctx, capi, oracle, graphs, name, dim, path):
+    A = _graph(graphs, name)
+    n = A.shape[0]
+    if path == 2 and n > 1024:
+        pytest.skip("on-chip path holds at most 1024 vertices")
+    x0 = capi.reference_uniform(17, n * dim).reshape(n, dim)
+    F_ref, S = oracle.flat_forces(A, dim, x0)
+    F = ctx.flat_forces(A, dim, x0, capi.flat_params(precision=capi.GE_F32), path=path)
+    assert force_error(F, F_ref, S).max() < TOL_F32
+
+
+@pytest.mark.parametrize("kw", [dict(use_weights=0), dict(linlog=1), dict(nohubs=1), dict(delta=0.5),
+                                dict(delta=0.0), dict(ks=0.3, ksmax=2.0, repel=2.0, attract=0.7, gravity=1.5, tolerate=0.8)])
+@pytest.mark.parametrize("path", [1, 2])
+def test_forces_options(ctx, capi, oracle, graphs, kw, path):
+    A = _graph(graphs, "galerkin")
+    n = A.shape[0]
+    x0 = capi.reference_uniform(5, n * 2).reshape(n, 2)
+    okw = {"useWeights" if k == "use_weights" else k: v for k, v in kw.items()}
+    F_ref, S = oracle.flat_forces(A, 2, x0, oracle.Params(**okw))
+    F = ctx.flat_forces(A, 2, x0, capi.flat_params(**kw), path=path)
+    assert force_error(F, F_ref, S).max() < TOL_F64
+
+
+def test_coincident_points_and_padding(ctx, capi, oracle, graphs):
+    """eps clamp (include/forceatlas.hpp:155-157) and tile padding: n not a multiple of 256."""
+    A = graphs.grid2d(9, 29)  # n = 261
+    n = A.shape[0]
+    x0 = capi.reference_uniform(1, n * 2).reshape(n, 2)
+    x0[10] = x0[11]          # distance 0 -> clamped, direction 0
+    x0[20] = x0[21] + 1e-7   # below eps
+    F_ref, S = oracle.flat_forces(A, 2, x0)
+    for path in (1, 2):
+        F = ctx.flat_forces(A, 2, x0, capi.flat_params(), path=path)
+        assert np.isfinite(F).all()
+        assert force_error(F, F_ref, S).max() < TOL_F64
+
+
+@pytest.mark.parametrize("k", [1, 5, 25])
+@pytest.mark.parametrize("path", ["tiled", "onchip"])
+def test_positions_after_k_iterations(ctx, capi, oracle, k, path, monkeypatch):
+    """Golden positions of the compiled reference after k iterations.  Trajectories amplify
+    rounding differences, so the bound widens with k (1e-12 per step would already be generous for
+    a contracting map; 1e-9 at k=25 leaves room for the speed-cap discontinuity)."""
+    A, z = load_flat_golden()
+    monkeypatch.setenv("GE_ONCHIP_MAX", "0" if path == "tiled" else "1024")
+    for dim in (2, 3):
+        x = ctx.flat_forceatlas(A, dim, z["x0_d%d" % dim], capi.flat_params(iterations=k))
+        ref = z["x_d%d_k%d" % (dim, k)]
+        assert np.abs(x - ref).max() < {1: 1e-12, 5: 1e-11, 25: 1e-9}[k], np.abs(x - ref).max()
+
+
+def test_normalize_option(ctx, capi, oracle, monkeypatch):
+    A, z = load_flat_golden()
+    for path in ("0", "1024"):
+        monkeypatch.setenv("GE_ONCHIP_MAX", path)
+        x = ctx.flat_forceatlas(A, 2, z["x0_d2"], capi.flat_params(iterations=7, normalize=1))
+        assert np.abs(x - z["x_d2_k7_normalize"]).max() < 1e-10
+        assert abs(np.linalg.norm(x, axis=1).max() - 1.0) < 1e-12
+
+
+def test_origin_vertex_gives_nan_like_reference(ctx, capi, graphs):
+    """include/forceatlas.hpp:205 divides by |x_i| unclamped: a vertex at the origin goes NaN."""
+    A = graphs.grid2d(3, 3)
+    x0 = capi.reference_uniform(2, 18).reshape(9, 2)
+    x0[4] = 0.0
+    for path in (1, 2):
+        F = ctx.flat_forces(A, 2, x0, capi.flat_params(), path=path)
+        assert np.isnan(F[4]).all() and np.isfinite(np.delete(F, 4, axis=0)).all()
+
+
+def test_plan_row_blocks_equal_full(ctx, capi, oracle, graphs):
+    """Row-block sharding (multi-GPU layout): two plans owning half the rows each reproduce the
+    single-plan forces and positions exactly."""
+    A = graphs.rgg(1500, 10.0, seed=4)
+    n = A.shape[0]
+    x0 = capi.reference_uniform(9, n * 2).reshape(n, 2)
+    p = capi.flat_params()
+    full = ctx.flat_plan(A, 2, p)
+    full.upload(x0)
+    full.iterate(1)
+    x_full, f_full = full.download(), full.download_forces()
+    half = n // 2
+    xs = []
+    for rows in ((0, half), (half, n)):
+        pl = ctx.flat_plan(A, 2, p, rows=rows)
+        pl.upload(x0)
+        pl.iterate(1)
+        assert np.array_equal(pl.download_forces(), f_full[rows[0]:rows[1]])
+        xs.append(pl.download()[rows[0]:rows[1]])
+    assert np.array_equal(np.vstack(xs), x_full)
+
+
+def test_full_size_properties(ctx, capi, oracle, graphs):
+    """BASELINE config 4 size (n = 500 000, all pairs, d = 2) through size-independent properties:
+    (1) Newton's third law: repulsion and attraction are antisymmetric, so the forces minus the
+        gravity term sum to zero; (2) 48 sampled rows agree with the oracle to 1e-10."""
+    n = 500_000
+    A = graphs.rgg(n, 10.0, seed=7)
+    n = A.shape[0]
+    x0 = capi.reference_uniform(23, n * 2).reshape(n, 2)
+    F = ctx.flat_forces(A, 2, x0, capi.flat_params(), path=1)
+    assert np.isfinite(F).all()
+    deg = np.asarray(A.sum(axis=1)).ravel()
+    grav = -x0 / np.linalg.norm(x0, axis=1, keepdims=True) * (deg + 1)[:, None]
+    net = (F - grav).sum(axis=0)
+    assert np.abs(net).max() < 1e-9 * np.abs(F - grav).sum()
+    rows = np.random.default_rng(0).choice(n, 48, replace=False)
+    for r in rows:
+        F_ref, S = oracle.flat_forces(A, 2, x0, rows=(int(r), int(r) + 1))
+        assert np.linalg.norm(F[r] - F_ref[r]) / S[r] < TOL_F64

@@ -1,0 +1,165 @@
+"""GPU parity of the per-aggregate solver (K2: singleton / warp / CTA / segmented tiers), the
+prolongation epilogue and the whole embed() driver, through the C ABI."""
+import numpy as np
+import pytest
+
+from helpers import TOL_F32, TOL_F64, force_error, layout_stats, load_hier_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(graphs, name):
+    if name == "grid30":            # the reference partitioner's own hierarchy (sizes <= 8)
+        As, Ps, _ = load_hier_golden()
+        return As, Ps
+    if name == "rgg_big_aggs":      # coarsening 0.02: aggregates of 30..150 members -> CTA tier
+        return graphs.coarsen(graphs.rgg(4000, 10.0, seed=3), 0.02, min_coarse=20)
+    if name == "rmat":              # skewed sizes
+        return graphs.coarsen(graphs.rmat(12, 8, seed=2), 0.25, min_coarse=40)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["grid30", "rgg_big_aggs", "rmat"])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("cta_max", [512, 40])
+def test_forces_fp64(ctx, capi, oracle, graphs, name, dim, cta_max, monkeypatch):
+    """cta_max=40 pushes every aggregate above 40 members through the segmented multi-CTA tier."""
+    monkeypatch.setenv("GE_CTA_MAX", str(cta_max))
+    As, Ps = _case(graphs, name)
+    rng = np.random.default_rng(1)
+    for l in range(min(2, len(Ps))):
+        A, P = As[l], Ps[l]
+        n, m = A.shape[0], P.shape[0]
+        cA = rng.normal(size=(m, dim))
+        x = capi.reference_uniform(3 + l, n * dim).reshape(n, dim)
+        _, F_ref, S = oracle.multilevel_run(A, P, cA, np.ones(m), dim, x, oracle.Params(iterations=1), forces_iter=0)
+        F = ctx.multilevel_forces(A, P, cA, x, dim, capi.multilevel_params())
+        err = force_error(F, F_ref, S)
+        assert err.max() < TOL_F64, (l, err.max(), np.argmax(err))
+
+
+def test_forces_fp32(ctx, capi, oracle, graphs):
+    As, Ps = _case(graphs, "rgg_big_aggs")
+    A, P = As[0], Ps[0]
+    n, m = A.shape[0], P.shape[0]
+    cA = np.random.default_rng(1).normal(size=(m, 2))
+    x = capi.reference_uniform(3, n * 2).reshape(n, 2)
+    _, F_ref, S = oracle.multilevel_run(A, P, cA, np.ones(m), 2, x, oracle.Params(iterations=1), forces_iter=0)
+    F = ctx.multilevel_forces(A, P, cA, x, 2, capi.multilevel_params(precision=capi.GE_F32))
+    assert force_error(F, F_ref, S).max() < TOL_F32
+
+
+def test_quirk_q1_edge_dropped(ctx, capi, oracle):
+    """include/forceatlas.hpp:417 compares the global neighbour id with the LOCAL member index:
+    with aggregate {1,0,2} (member order 1,0,2) vertex 1 (local 0) loses its edge to global 0."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(np.array([[0, 1, 1, 0], [1, 0, 1, 1], [1, 1, 0, 0], [0, 1, 0, 0]], dtype=float))
+    P = sp.csr_matrix((np.ones(4), [1, 0, 2, 3], [0, 3, 4]), shape=(2, 4))
+    cA = np.array([[0.0, 0.0], [2.0, 1.0]])
+    x = capi.reference_uniform(4, 8).reshape(4, 2)
+    _, F_ref, S = oracle.multilevel_run(A, P, cA, np.ones(2), 2, x, oracle.Params(iterations=1), forces_iter=0)
+    F = ctx.multilevel_forces(A, P, cA, x, 2, capi.multilevel_params())
+    assert force_error(F, F_ref, S).max() < TOL_F64
+
+
+@pytest.mark.parametrize("name", ["grid30", "rgg_big_aggs", "rmat"])
+@pytest.mark.parametrize("k", [1, 3])
+@pytest.mark.parametrize("cta_max", [512, 40])
+def test_positions_after_k_iterations(ctx, capi, oracle, graphs, name, k, cta_max, monkeypatch):
+    """k iterations + centre/normalise/prolongation from the SAME initial local coordinates."""
+    monkeypatch.setenv("GE_CTA_MAX", str(cta_max))
+    As, Ps = _case(graphs, name)
+    A, P = As[0], Ps[0]
+    n, m = A.shape[0], P.shape[0]
+    rng = np.random.default_rng(2)
+    cA, rA = rng.normal(size=(m, 2)), rng.random(m) * 0.3 + 0.05
+    init = oracle.multilevel_init(P, 2, 5)
+    ref = oracle.multilevel_run(A, P, cA, rA, 2, init, oracle.Params(iterations=k))
+    x = ctx.multilevel_forceatlas(A, P, cA, rA, 2, capi.multilevel_params(iterations=k), init=init)
+    assert np.abs(x - ref).max() < 1e-10, np.abs(x - ref).max()
+
+
+def test_seeded_init_matches_reference_stream(ctx, capi, oracle):
+    """init=NULL draws the reference's stream (forceatlas.hpp:341,356-358) from params.seed: the
+    result equals the golden output of the COMPILED REFERENCE for the same seed (k=1,3)."""
+    As, Ps, z = load_hier_golden()
+    for dim in (2, 3):
+        for l in (0, 1):
+            for k in (1, 3):
+                cA, rA = z["ml_cA_l%d_d%d" % (l, dim)], z["ml_rA_l%d_d%d" % (l, dim)]
+                x = ctx.multilevel_forceatlas(As[l], Ps[l], cA, rA, dim, capi.multilevel_params(iterations=k, seed=5))
+                assert np.abs(x - z["ml_x_l%d_d%d_k%d" % (l, dim, k)]).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["grid30", "rgg_big_aggs", "rmat"])
+def test_prolongation_properties_100_iterations(ctx, capi, oracle, graphs, name):
+    """Exact properties of forceatlas.hpp:539-569 after the full 100 iterations: every member lies in
+    its parent ball, the farthest member of a multi-member aggregate lies ON it, the members'
+    centroid is the parent centre, singletons sit exactly on it; and the layout statistics agree
+    with the oracle's run from the same initial coordinates."""
+    As, Ps = _case(graphs, name)
+    A, P = As[0], Ps[0]
+    n, m = A.shape[0], P.shape[0]
+    rng = np.random.default_rng(2)
+    cA, rA = rng.normal(size=(m, 2)) * 5, rng.random(m) * 0.3 + 0.05
+    init = oracle.multilevel_init(P, 2, 5)
+    x = ctx.multilevel_forceatlas(A, P, cA, rA, 2, capi.multilevel_params(), init=init)
+    assert np.isfinite(x).all()
+    v_A = capi.vertex_to_aggregate(P)
+    d = np.linalg.norm(x - cA[v_A], axis=1)
+    assert (d <= rA[v_A] * (1 + 1e-12)).all()
+    size = np.diff(P.indptr)
+    far = np.zeros(m)
+    np.maximum.at(far, v_A, d)
+    multi = size > 1
+    assert np.allclose(far[multi], rA[multi], rtol=1e-12)
+    assert np.array_equal(x[P.indices[P.indptr[:-1][~multi]]], cA[~multi])
+    cent = np.zeros((m, 2))
+    np.add.at(cent, v_A, x)
+    assert np.abs(cent / size[:, None] - cA).max() < 1e-9
+    ref = oracle.multilevel_run(A, P, cA, rA, 2, init, oracle.Params(iterations=100))
+    s1, s2 = layout_stats(A, x), layout_stats(A, ref)
+    for key in s1:
+        assert abs(s1[key] - s2[key]) < 0.05 * abs(s2[key]), (key, s1, s2)
+
+
+def test_embed_against_reference_golden(ctx, capi, oracle):
+    """partition::embed on the reference partitioner's hierarchy (grid 30x30, 3 levels, 100 000
+    coarsest iterations).  Trajectories are chaotic, so the layouts are compared on statistics
+    (tolerance 20 %) against the golden output of the compiled reference."""
+    As, Ps, z = load_hier_golden()
+    x, st = ctx.embed(As, Ps, 2, seed=21)
+    assert np.isfinite(x).all() and st["kernel_launches"] > 0
+    assert st["pair_interactions"] == pytest.approx(
+        100000 * 16 * 15 + 100 * sum(int((np.diff(P.indptr) * (np.diff(P.indptr) - 1)).sum()) for P in Ps))
+    s1, s2 = layout_stats(As[0], x), layout_stats(As[0], z["embed_d2_seed21"])
+    for key in s1:
+        assert abs(s1[key] - s2[key]) < 0.2 * abs(s2[key]), (key, s1, s2)
+
+
+def test_embed_short_run_matches_oracle(ctx, capi, oracle):
+    """With few iterations per level the whole driver (flat init stream, radii, rescale, multilevel
+    init stream, prolongation) is comparable position by position with the oracle's embed()."""
+    As, Ps, _ = load_hier_golden()
+    for dim in (2, 3):
+        ref = oracle.embed(As, Ps, dim, seed=9, coarse_iterations=20, level_iterations=3)
+        x, _ = ctx.embed(As, Ps, dim, seed=9, coarse_iterations=20, level_iterations=3)
+        assert np.abs(x - ref).max() < 1e-8 * np.abs(ref).max(), np.abs(x - ref).max()
+
+
+def test_config2_full_size_properties(ctx, capi, graphs):
+    """BASELINE config 2 (RGG, n = 100 000, avg degree 10, d = 2, coarsening 0.25): NaN-free and
+    every vertex inside the ball of its aggregate at the finest level."""
+    A = graphs.rgg(100_000, 10.0, seed=12345)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=100)
+    x, st = ctx.embed(As, Ps, 2, seed=1)
+    assert np.isfinite(x).all()
+    assert x.shape == (A.shape[0], 2)
+    v_A = capi.vertex_to_aggregate(Ps[0])
+    # aggregates are compact relative to the layout: mean member-to-centroid distance is small
+    cent = np.zeros((Ps[0].shape[0], 2))
+    np.add.at(cent, v_A, x)
+    cent /= np.diff(Ps[0].indptr)[:, None]
+    spread = np.linalg.norm(x - cent[v_A], axis=1).mean()
+    extent = np.linalg.norm(x - x.mean(0), axis=1).max()
+    assert spread < 0.05 * extent

@@ -1,0 +1,49 @@
+"""The oracle against the compiled reference itself (oracle/_ref, built from the unmodified
+sources under /root/reference).  Only runs where the reference was compiled; the committed golden
+vectors (test_oracle_golden.py) carry the same pin to boxes without /root/reference."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    if not oracle.ref_available("strict"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return oracle
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_flat_bitwise_any_thread_count(ref, graphs, dim, nthreads):
+    A = graphs.rgg(300, 8.0, seed=3)
+    n = A.shape[0]
+    x0 = ref.mt_uniform(11, n * dim).reshape(n, dim)
+    for k in (1, 10):
+        p = ref.Params(iterations=k)
+        xo, _ = ref.flat_run(A, dim, x0, p)
+        assert np.array_equal(xo, ref.ref_flat(A, dim, x0, p, nthreads=nthreads))
+
+
+@pytest.mark.parametrize("kw", [dict(useWeights=False), dict(linlog=True), dict(delta=0.0), dict(delta=2.0),
+                                dict(ks=0.3, ksmax=2.0, repel=2.0, attract=0.7, gravity=1.5, tolerate=0.8)])
+def test_flat_options(ref, graphs, kw):
+    A = graphs.galerkin(graphs.grid2d(10, 10), graphs.coarsen(graphs.grid2d(10, 10), 0.5, 10)[1][0])
+    n = A.shape[0]  # weighted, with self-loops (quirk Q5)
+    x0 = ref.mt_uniform(2, n * 2).reshape(n, 2)
+    p = ref.Params(iterations=9, **kw)
+    xo, _ = ref.flat_run(A, 2, x0, p)
+    assert np.array_equal(xo, ref.ref_flat(A, 2, x0, p))
+
+
+def test_multilevel_and_embed_with_own_hierarchy(ref, graphs):
+    A = graphs.rgg(800, 9.0, seed=5)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=20)
+    rng = np.random.default_rng(0)
+    for l in range(len(Ps)):
+        m = Ps[l].shape[0]
+        cA, rA = rng.normal(size=(m, 3)), rng.random(m)
+        p = ref.Params(iterations=20)
+        xo = ref.multilevel_run(As[l], Ps[l], cA, rA, 3, ref.multilevel_init(Ps[l], 3, 8), p)
+        assert np.array_equal(xo, ref.ref_multilevel(As[l], Ps[l], cA, rA, 3, p, seed=8))
+    xr, _ = ref.ref_embed(As, Ps, 2, seed=13)
+    assert np.array_equal(ref.embed(As, Ps, 2, seed=13), xr)
