@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- ForceAtlas iterations/s and pair-interactions/s on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Workload (config.workload): BASELINE config 4, the flat single-level ForceAtlas iteration on a
+500 000-vertex random geometric graph (avg degree 10), all-pairs repulsion, d = 2, FP64 like the
+reference.  It is the configuration the metric (iterations/s, pair-interactions/s at 1/2/4/8 B200)
+is quoted on, it fits one GPU, and it is the path that shards (row blocks + one coordinate
+all-gather per iteration), so the same workload is measured at every N ("scaling": "strong").
+A step = one ForceAtlas iteration (include/forceatlas.hpp:146-270) over the whole graph.
+At N = 1 the same run also reports embed() wall time on BASELINE config 2 (RGG 100k, multilevel,
+d = 2) under "embed", and the FP32 variant of the flat kernels under "fp32".
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json (driver-measured copy bandwidth)"
+    return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def algorithmic(n, nnz, dim, w):
+    """5d+4 flops per ordered pair; attraction+step bytes per iteration =
+    nnz*(4+w) [indices+weights] + n*(4 + w + 5*d*w) [indptr, mass; own coords, repulsion sum,
+    previous force read; new coords, previous force written]."""
+    return dict(pairs=float(n) * (n - 1), flops_per_pair=5 * dim + 4,
+                step_bytes=float(nnz) * (4 + w) + float(n) * (4 + w + 5 * dim * w))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms)."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+            0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else \
+                    pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add("sampler_error:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def flat_graph(n, seed=7):
+    entry.load_package()
+    from graph_embed_b200 import graphs
+    t = time.time()
+    A = graphs.rgg(n, 10.0, seed=seed)
+    log("[bench] rgg n=%d nnz=%d (%.1fs)" % (A.shape[0], A.nnz, time.time() - t))
+    return A
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_flat_rate(O, dim, n_sample, iters, threads, kind):
+    """pair-interactions/s of partition::forceAtlas on an n_sample-vertex graph of the same
+    generator; returns (rate, seconds)."""
+    from graph_embed_b200 import graphs
+    A = graphs.rgg(n_sample, 10.0, seed=7)
+    n = A.shape[0]
+    x0 = O.mt_uniform(23, n * dim).reshape(n, dim)
+    t = time.time()
+    if kind == "reference":
+        O.ref_flat(A, dim, x0, O.Params(iterations=iters), nthreads=threads, kind="fast")
+    else:
+        O.flat_run(A, dim, x0, O.Params(iterations=iters))
+    dt = time.time() - t
+    return float(n) * (n - 1) * iters / dt, dt, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    entry.load_package()
+    O = entry.load_oracle()
+    kind = "reference" if O.ref_available("fast") else "port"
+    threads = O.ref_lib("fast").ref_max_threads() if kind == "reference" else 1
+    n_sample = args.ref_n
+    for _ in range(args.warmup):
+        cpu_flat_rate(O, args.dim, n_sample, 1, threads, kind)
+    t_total, pairs_total, n_eff = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        rate, dt, n_eff = cpu_flat_rate(O, args.dim, n_sample, 1, threads, kind)
+        t_total += dt
+        pairs_total += rate * dt
+    value = pairs_total / t_total
+    sample = ("flat forceAtlas, 1 iteration per step on a %d-vertex RGG (avg degree 10) from the "
+              "same generator as the %d-vertex workload; pair-interactions/s is size-independent "
+              "for the O(n^2) kernel" % (n_eff, args.n))
+    line = {"impl": "reference", "metric": "forceatlas_pair_interactions_per_sec", "value": value,
+            "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "iters_per_sec_at_workload_n": value / (float(args.n) * (args.n - 1)),
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": threads,
+                             "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "config4: flat single-level ForceAtlas, RGG n=%d avg degree 10, all-pairs "
+                        "repulsion, dim=%d" % (args.n, args.dim),
+            "n": args.n, "dim": args.dim, "avg_degree": 10,
+            "parallelism": "row-block x%d + coordinate all-gather per iteration" % args.gpus
+            if args.gpus > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB device write outside the timed events)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    entry.load_package()
+    from graph_embed_b200 import capi, graphs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path is the only path (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    dev = torch.device("cuda", local)
+    # a non-default stream: the library launches on it, torch/NCCL order against it, and the CUDA
+    # events of the timed region are recorded on it (torch.cuda.Event sees only this stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = capi.Context(local, stream=stream.cuda_stream)
+
+    A = flat_graph(args.n)
+    n, nnz, dim = A.shape[0], A.nnz, args.dim
+    prec = capi.GE_F64
+    w = 8
+    alg = algorithmic(n, nnz, dim, w)
+    params = capi.flat_params(precision=prec)
+    x0 = capi.reference_uniform(23, n * dim).reshape(n, dim)
+
+    # row blocks: ld is a multiple of 256, hence of every N in {1,2,4,8}
+    probe_ld = ((n + 255) // 256) * 256
+    R = probe_ld // world
+    r0, r1 = min(n, rank * R), min(n, (rank + 1) * R)
+    plan = ctx.flat_plan(A, dim, params, rows=(r0, r1))
+    ld = plan.ld
+    assert ld == probe_ld
+    tdt = torch.float64
+    bufs = [torch.zeros(dim * ld, dtype=tdt, device=dev) for _ in range(2)]
+    plan.bind_coords(bufs[0].data_ptr(), bufs[1].data_ptr())
+    plan.upload(x0)
+    ptr_to_buf = {bufs[0].data_ptr(): bufs[0], bufs[1].data_ptr(): bufs[1]}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step():
+        plan.launch_iteration()
+        if world > 1:
+            nxt = ptr_to_buf[plan.next_ptr()].view(dim, ld)
+            for k in range(dim):  # in-place: own slice sits at rank*R of the output
+                dist.all_gather_into_tensor(nxt[k], nxt[k, rank * R:(rank + 1) * R])
+        plan.swap()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.time()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)  # evict L2 between timed steps (outside the event pair)
+        ev[s][0].record(stream)
+        one_step()
+        ev[s][1].record(stream)
+    barrier()
+    t_wall = time.time() - t_wall
+    launches = ctx.launches - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.result()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = alg["pairs"] * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device time (CUDA events inside the library, on the launching stream) -------
+    plan.profile(True)
+    for _ in range(3):
+        flush.fill_(1)
+        one_step()
+    barrier()
+    prof = plan.profile_get()
+    plan.profile(False)
+    rep_ms = prof["repulsion_ms"] / max(prof["repulsion_launches"], 1)
+    step_ms = prof["attract_step_ms"] / max(prof["attract_step_launches"], 1)
+    rows_frac = (r1 - r0) / float(n)
+    hbm_peak, hbm_src = measured_peaks()
+    out = None
+    if rank == 0:
+        fp64_peak = ctx.fma_peak_tflops(capi.GE_F64)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("k_repulsion_f64_d%d_bytes_per_launch" % dim)
+        rep_flops = alg["pairs"] * rows_frac * alg["flops_per_pair"]
+        roof = {"kernel": "k_repulsion<double,%d>" % dim, "bound": "fp64", "unit": "TFLOP/s",
+                "achieved": rep_flops / (rep_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                "peak_source": "measured live: ge_measure_fma_peak (independent DFMA chains, all SMs, CUDA events)",
+                "traffic": traffic, "ms_per_launch": rep_ms, "share_of_step": rep_ms / (rep_ms + step_ms),
+                "pairs_per_launch": alg["pairs"] * rows_frac, "flops_per_pair": alg["flops_per_pair"]}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        step_bytes = alg["step_bytes"] * rows_frac
+        roof2 = {"kernel": "k_attract_step<double,%d>" % dim, "bound": "hbm", "unit": "GB/s",
+                 "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_source": hbm_src,
+                 "traffic": None, "ms_per_launch": step_ms, "bytes_per_launch": step_bytes}
+        roof2["frac"] = roof2["achieved"] / roof2["peak"]
+        out = {"metric": "forceatlas_pair_interactions_per_sec", "value": value,
+               "unit": "pair-interactions/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "iters_per_sec": 1e3 / ms_per_step, "wall_s_timed_region": t_wall,
+               "config": workload_config(args), "gpu_launches": launches, "clocks": clocks,
+               "roofline": roof, "roofline_attraction": roof2}
+
+    # ---- e2e: host buffers in, host buffers out, every step -------------------------------------
+    e2e = bench_e2e(args, torch, dist, capi, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier)
+    if rank == 0:
+        out["e2e"] = e2e
+
+    if rank == 0 and world == 1:
+        out["fp32"] = bench_fp32(args, capi, ctx, A, x0, alg)
+        if not args.no_attraction:
+            out["roofline_attraction_large"] = bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src)
+        if not args.no_embed:
+            out["embed"] = bench_embed(args, capi, ctx, graphs)
+        if not args.no_cpu:
+            out["cpu_baseline"] = bench_cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_e2e(args, torch, dist, capi, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier):
+    """Same metric through the public host-buffer API, host<->device copies inside the timed
+    region.  N = 1: ge_flat_forceatlas (the forceAtlas drop-in: graph + coordinates in from pinned
+    host memory, coordinates out), one call per step.  N > 1: the row-block plan API with the
+    coordinates uploaded and downloaded every step (the graph stays resident)."""
+    n, dim = A.shape[0], args.dim
+    steps = max(2, min(args.steps, 5))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    x = pin(x0.copy())
+    h0, d0 = ctx.bytes_moved
+    if world == 1:
+        import scipy.sparse as sp
+        Ap = sp.csr_matrix((pin(A.data), pin(A.indices), pin(A.indptr)), shape=A.shape)
+        p1 = capi.flat_params(iterations=1)
+        ctx.flat_forceatlas(Ap, dim, x, p1)  # warm-up
+        barrier()
+        h0, d0 = ctx.bytes_moved
+        t = time.time()
+        for _ in range(steps):
+            ctx.flat_forceatlas(Ap, dim, x, p1, inplace=True)
+        dt = time.time() - t
+        note = "ge_flat_forceatlas(host CSR, host coords, iterations=1) per step"
+    else:
+        plan.upload(x)
+        barrier()
+        h0, d0 = ctx.bytes_moved
+        t = time.time()
+        for _ in range(steps):
+            plan.upload(x)
+            plan.launch_iteration()
+            nxt = ptr_to_buf[plan.next_ptr()].view(dim, ld)
+            for k in range(dim):
+                dist.all_gather_into_tensor(nxt[k], nxt[k, rank * R:(rank + 1) * R])
+            plan.swap()
+            x = plan.download()
+        barrier()
+        dt = time.time() - t
+        note = "flat plan: upload coords, iterate own rows, all-gather, download coords per step"
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    h1, d1 = ctx.bytes_moved
+    return {"value": alg["pairs"] * steps / dt, "unit": "pair-interactions/s", "steps": steps,
+            "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": (h1 - h0) / steps,
+            "d2h_bytes_per_step": (d1 - d0) / steps, "api": note, "host_memory": "pinned"}
+
+
+def bench_fp32(args, capi, ctx, A, x0, alg):
+    """FP32 variant of the same kernels (reduced precision: reported beside, never as, the headline)."""
+    n, dim = A.shape[0], args.dim
+    plan = ctx.flat_plan(A, dim, capi.flat_params(precision=capi.GE_F32))
+    plan.upload(x0)
+    plan.iterate(3)
+    plan.sync()
+    plan.profile(True)
+    plan.iterate(5)
+    prof = plan.profile_get()
+    plan.close()
+    rep_ms = prof["repulsion_ms"] / prof["repulsion_launches"]
+    step_ms = prof["attract_step_ms"] / prof["attract_step_launches"]
+    peak = ctx.fma_peak_tflops(capi.GE_F32)
+    ach = alg["pairs"] * alg["flops_per_pair"] / (rep_ms * 1e-3) / 1e12
+    return {"dtype": "f32", "pair_interactions_per_sec": alg["pairs"] / ((rep_ms + step_ms) * 1e-3),
+            "iters_per_sec": 1e3 / (rep_ms + step_ms),
+            "roofline": {"kernel": "k_repulsion<float,%d>" % dim, "bound": "fp32", "unit": "TFLOP/s",
+                         "achieved": ach, "peak": peak, "frac": ach / peak, "ms_per_launch": rep_ms,
+                         "peak_source": "measured live: ge_measure_fma_peak"}}
+
+
+def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
+    """The CSR attraction + step kernel alone on a graph whose arrays exceed L2 (n = 2M-vertex RGG,
+    ~20M entries, ~0.5 GB of algorithmic traffic): achieved HBM GB/s against the measured copy bandwidth."""
+    n = args.attr_n
+    t = time.time()
+    A = graphs.rgg(n, 10.0, seed=11)
+    n, nnz, dim = A.shape[0], A.nnz, 3
+    log("[bench] attraction graph n=%d nnz=%d (%.1fs)" % (n, nnz, time.time() - t))
+    out = {}
+    for prec, w, name in ((capi.GE_F64, 8, "f64"), (capi.GE_F32, 4, "f32")):
+        plan = ctx.flat_plan(A, dim, capi.flat_params(precision=prec))
+        plan.upload(capi.reference_uniform(5, n * dim).reshape(n, dim))
+        plan.select_kernels(2)  # attraction + step only: 4e12 ordered pairs per repulsion pass here
+        plan.iterate(2)
+        plan.sync()
+        plan.profile(True)
+        plan.iterate(5)
+        prof = plan.profile_get()
+        plan.close()
+        ms = prof["attract_step_ms"] / prof["attract_step_launches"]
+        b = algorithmic(n, nnz, dim, w)["step_bytes"]
+        out[name] = {"kernel": "k_attract_step<%s,3>" % ("double" if w == 8 else "float"), "bound": "hbm",
+                     "unit": "GB/s", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                     "frac": b / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms,
+                     "bytes_per_launch": b, "n": n, "nnz": nnz, "edge_visits_per_sec": nnz / (ms * 1e-3)}
+    return out
+
+
+def bench_embed(args, capi, ctx, graphs):
+    """BASELINE config 2: embed() wall time, bracketed like examples/embedder.cpp:219-222
+    (hierarchy already built, coordinates returned to the host)."""
+    t = time.time()
+    A = graphs.rgg(100_000, 10.0, seed=12345)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=100)
+    log("[bench] config2 hierarchy %s (%.1fs)" % ([a.shape[0] for a in As], time.time() - t))
+    ctx.embed(As, Ps, 2, seed=1, coarse_iterations=1000)  # warm-up
+    walls, st = [], None
+    for rep in range(3):
+        t = time.time()
+        x, st = ctx.embed(As, Ps, 2, seed=1 + rep)
+        walls.append(time.time() - t)
+    assert np.isfinite(x).all()
+    wall = float(np.median(walls))
+    out = {"workload": "config2: RGG n=%d avg degree 10, multilevel embed, dim=2, coarsening 0.25, "
+                       "levels %s" % (As[0].shape[0], [a.shape[0] for a in As]),
+           "embed_wall_s": wall, "pair_interactions": st["pair_interactions"],
+           "pair_interactions_per_sec": st["pair_interactions"] / wall,
+           "iterations": 100000 + 100 * len(Ps), "iters_per_sec": (100000 + 100 * len(Ps)) / wall,
+           "coarse_ms": st["coarse_ms"], "levels_ms": st["levels_ms"], "host_radii_ms": st["host_radii_ms"],
+           "kernel_launches": st["kernel_launches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]}
+    if not args.no_cpu:
+        O = entry.load_oracle()
+        if O.ref_available("fast"):
+            threads = O.ref_lib("fast").ref_max_threads()
+            best = None
+            for nt in sorted({1, threads}):
+                _, secs = O.ref_embed(As, Ps, 2, seed=1, nthreads=nt, kind="fast")
+                if best is None or secs < best[0]:
+                    best = (secs, nt)
+            out["cpu_reference_embed_wall_s"], out["cpu_reference_threads"] = best
+    return out
+
+
+def bench_cpu_baseline(args):
+    """The reference's own flat forceAtlas (oracle/_ref, -O3, OpenMP, all host threads) on a bounded
+    sample of the same workload, ~10-30 s of CPU work."""
+    O = entry.load_oracle()
+    kind = "reference" if O.ref_available("fast") else "port"
+    threads = O.ref_lib("fast").ref_max_threads() if kind == "reference" else 1
+    rate, dt, n = cpu_flat_rate(O, args.dim, 6000, 1, threads, kind)      # calibrate
+    n_sample = int(min(60000, max(8000, (rate * 15.0 / 2) ** 0.5)))        # ~15 s for 2 iterations
+    rate, dt, n = cpu_flat_rate(O, args.dim, n_sample, 2, threads, kind)
+    return {"value": rate, "unit": "pair-interactions/s", "cores": threads, "kind": kind,
+            "seconds": dt,
+            "sample": "flat forceAtlas, 2 iterations on a %d-vertex RGG (avg degree 10) of the same "
+                      "generator; the O(n^2) kernel's pair rate is size-independent" % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=500_000)
+    ap.add_argument("--dim", type=int, default=2)
+    ap.add_argument("--ref-n", type=int, default=30_000)
+    ap.add_argument("--attr-n", type=int, default=2_000_000)
+    ap.add_argument("--no-embed", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-attraction", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

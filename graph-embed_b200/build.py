@@ -47,7 +47,8 @@ def build_library(verbose=False, force=False):
             cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static"])
+        subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB]
+                              + objs + ["-cudart", "static"])
     return LIB
 
 

@@ -58,13 +58,14 @@ class EmbedStats(C.Structure):
 SYMBOLS = [
     "ge_version", "ge_last_error", "ge_params_default_flat", "ge_params_default_multilevel",
     "ge_embed_options_default", "ge_context_create", "ge_context_destroy",
-    "ge_context_launch_count", "ge_flat_forceatlas", "ge_multilevel_forceatlas", "ge_embed",
+    "ge_context_launch_count", "ge_context_bytes", "ge_measure_fma_peak",
+    "ge_flat_forceatlas", "ge_multilevel_forceatlas", "ge_embed",
     "ge_flat_forces", "ge_multilevel_forces", "ge_level_radii", "ge_reference_uniform",
     "ge_flat_plan_create", "ge_flat_plan_destroy", "ge_flat_plan_ld", "ge_flat_plan_elem_size",
     "ge_flat_plan_bind_coords", "ge_flat_plan_upload_coords", "ge_flat_plan_download_coords",
     "ge_flat_plan_download_forces", "ge_flat_plan_cur_coords", "ge_flat_plan_next_coords",
     "ge_flat_plan_launch_iteration", "ge_flat_plan_swap", "ge_flat_plan_iterate",
-    "ge_flat_plan_sync", "ge_flat_plan_profile", "ge_flat_plan_profile_get",
+    "ge_flat_plan_sync", "ge_flat_plan_select_kernels", "ge_flat_plan_profile", "ge_flat_plan_profile_get",
 ]
 
 _lib = None
@@ -86,6 +87,7 @@ def lib():
         L.ge_flat_plan_next_coords.restype = C.c_void_p
         L.ge_reference_uniform.argtypes = [C.c_uint32, C.c_int64, _pd]
         L.ge_context_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ge_context_bytes.restype = None
         for name in ("ge_context_destroy", "ge_flat_plan_destroy", "ge_flat_plan_swap"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = None
@@ -189,10 +191,23 @@ class Context:
     def launches(self):
         return int(lib().ge_context_launch_count(self.h))
 
+    @property
+    def bytes_moved(self):
+        h2d, d2h = C.c_double(), C.c_double()
+        lib().ge_context_bytes(self.h, C.byref(h2d), C.byref(d2h))
+        return h2d.value, d2h.value
+
+    def fma_peak_tflops(self, precision=GE_F64):
+        t = C.c_double()
+        _check(lib().ge_measure_fma_peak(self.h, int(precision), C.byref(t)))
+        return t.value
+
     # -- the reference's kernels, host buffers ------------------------------------------------
-    def flat_forceatlas(self, A, dim, coords, params):
+    def flat_forceatlas(self, A, dim, coords, params, inplace=False):
         a = CsrView(A)
-        x = _f64(coords).reshape(A.shape[0], dim).copy()
+        x = _f64(coords).reshape(A.shape[0], dim)
+        if not inplace:
+            x = x.copy()
         _check(lib().ge_flat_forceatlas(self.h, a.ref(), int(dim), _ptr(x, _pd), C.byref(params)))
         return x
 
@@ -307,6 +322,9 @@ class FlatPlan:
 
     def sync(self):
         _check(lib().ge_flat_plan_sync(self.h))
+
+    def select_kernels(self, mask):
+        lib().ge_flat_plan_select_kernels(self.h, int(mask))
 
     def profile(self, enable=True):
         lib().ge_flat_plan_profile(self.h, int(enable))

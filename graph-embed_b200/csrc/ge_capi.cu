@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <random>
@@ -57,23 +58,72 @@ inline double dist(const double* a, const double* b, int dim) {
   return std::sqrt(sum);
 }
 
-void grow_balls(std::vector<Event>& ev, double* r_A, int m) {
-  std::make_heap(ev.begin(), ev.end());
+// ev: the events of one family; every vertex id in them has local[id] in [0, nloc).
+// Service order = repeatedly the largest (t, i, j) among the current keys, exactly the reference's
+// sort + pop_back; but only events incident to a vertex that just froze change key, and an event
+// whose two endpoints are frozen can never act again, so a lazy-deletion heap over per-vertex
+// incidence lists does it in O(E log E) instead of the reference's O(V E log E).
+struct HeapItem {
+  Event e;
+  int idx, ver;
+  bool operator<(const HeapItem& o) const { return e < o.e; }
+};
+
+void grow_balls(std::vector<Event>& ev, double* r_A, int m, const int* local, int nloc,
+                std::vector<int>& inc_ptr, std::vector<int>& inc, std::vector<int>& ver,
+                std::vector<HeapItem>& heap) {
+  const int E = (int)ev.size();
+  inc_ptr.assign(nloc + 1, 0);
+  for (const Event& e : ev) {
+    inc_ptr[local[e.i] + 1]++;
+    inc_ptr[local[e.j] + 1]++;
+  }
+  for (int v = 0; v < nloc; ++v) inc_ptr[v + 1] += inc_ptr[v];
+  inc.resize(2 * (size_t)E);
+  {
+    std::vector<int> fill(inc_ptr.begin(), inc_ptr.end() - 1);
+    for (int x = 0; x < E; ++x) {
+      inc[fill[local[ev[x].i]]++] = x;
+      inc[fill[local[ev[x].j]]++] = x;
+    }
+  }
+  ver.assign(E, 0);
+  heap.clear();
+  heap.reserve(2 * (size_t)E);
+  for (int x = 0; x < E; ++x) heap.push_back(HeapItem{ev[x], x, 0});
+  std::make_heap(heap.begin(), heap.end());
   int count = 0;
-  while (count < m && !ev.empty()) {
-    std::pop_heap(ev.begin(), ev.end());
-    const Event top = ev.back();
-    ev.pop_back();
-    const double reach = -top.t;
-    const bool live_i = r_A[top.i] <= 0.0, live_j = r_A[top.j] <= 0.0;
+  while (count < m && !heap.empty()) {
+    std::pop_heap(heap.begin(), heap.end());
+    const HeapItem top = heap.back();
+    heap.pop_back();
+    if (top.ver != ver[top.idx]) continue;  // superseded key
+    ver[top.idx] = -1;                       // served
+    const int i = top.e.i, j = top.e.j;
+    const bool live_i = r_A[i] <= 0.0, live_j = r_A[j] <= 0.0;
     if (!live_i && !live_j) continue;
-    const int fi = live_i ? top.i : -1, fj = live_j ? top.j : -1;
-    if (live_i) r_A[top.i] = reach;
-    if (live_j) r_A[top.j] = reach;
+    const double reach = -top.e.t;
+    if (live_i) r_A[i] = reach;
+    if (live_j) r_A[j] = reach;
     // a frozen ball stops growing: the partner must cover the remaining gap alone
-    for (Event& e : ev)
-      if (e.i == fi || e.j == fi || e.i == fj || e.j == fj) e.t = -(2 * (-e.t) - (-top.t));
-    std::make_heap(ev.begin(), ev.end());
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? live_i : live_j)) continue;
+      const int v = local[side == 0 ? i : j];
+      for (int q = inc_ptr[v]; q < inc_ptr[v + 1]; ++q) {
+        const int x = inc[q];
+        if (ver[x] < 0) continue;
+        Event& e = ev[x];
+        if (side == 1 && live_i && (e.i == i || e.j == i)) continue;  // already re-keyed once
+        e.t = -(2 * (-e.t) - (-top.e.t));
+        const int other = (e.i == (side == 0 ? i : j)) ? e.j : e.i;
+        if (r_A[other] > 0.0) {  // both ends frozen now: can never act again
+          ver[x] = -1;
+          continue;
+        }
+        heap.push_back(HeapItem{e, x, ++ver[x]});
+        std::push_heap(heap.begin(), heap.end());
+      }
+    }
     count += (live_i ? 1 : 0) + (live_j ? 1 : 0);
   }
 }
@@ -82,13 +132,17 @@ void grow_balls(std::vector<Event>& ev, double* r_A, int m) {
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                  const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac) {
   std::fill(r_A, r_A + m, 0.0);
+  std::vector<int> inc_ptr, inc, ver, local(std::max(m, 1));
+  std::vector<HeapItem> heap;
   if (P_T_c == nullptr) {  // :616-679
     std::vector<Event> ev;
     ev.reserve((size_t)m * (m > 0 ? m - 1 : 0) / 2);
-    for (int i = 0; i < m; ++i)
+    for (int i = 0; i < m; ++i) {
+      local[i] = i;
       for (int j = i + 1; j < m; ++j)
         ev.push_back(Event{-dist(coords_A + (size_t)i * dim, coords_A + (size_t)j * dim, dim) / 2, i, j});
-    grow_balls(ev, r_A, m);
+    }
+    grow_balls(ev, r_A, m, local.data(), m, inc_ptr, inc, ver, heap);
     return;
   }
   const int mc = P_T_c->rows;
@@ -105,6 +159,7 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
       continue;
     }
     ev.clear();
+    for (int c = PI[b]; c < PI[b + 1]; ++c) local[PJ[c]] = c - PI[b];
     for (int c = PI[b]; c < PI[b + 1]; ++c) {
       const int a = PJ[c];
       for (int kk = A_c->indptr[a]; kk < A_c->indptr[a + 1]; ++kk) {
@@ -113,7 +168,7 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
           ev.push_back(Event{-dist(coords_A + (size_t)a * dim, coords_A + (size_t)j * dim, dim) / 2, a, j});
       }
     }
-    grow_balls(ev, r_A, m);
+    grow_balls(ev, r_A, m, local.data(), s, inc_ptr, inc, ver, heap);
   }
   for (int b = 0; b < mc; ++b) {  // :757-777 shrink each family into its parent ball
     const double* cb = coords_Ac + (size_t)b * dim;
@@ -134,6 +189,47 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
 }
 
 namespace {
+
+// Independent register-resident FMA chains: the FP-pipe roofline the repulsion kernels are
+// measured against (SURVEY.md section 8d asks for a measured, not derived, denominator).
+template <typename T>
+__global__ void __launch_bounds__(512) k_fma_peak(T* out, int iters, T b, T c) {
+  T a[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = (T)(threadIdx.x + u) * (T)1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = fma(a[u], b, c);
+  }
+  T s = (T)0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s += a[u];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename T>
+double fma_peak(ge_context* ctx) {
+  const int threads = 512, ctas = ctx->sm_count * 4, iters = 1 << 15;
+  DevBuf<T> out(ctx, (size_t)threads * ctas);
+  cudaEvent_t e0, e1;
+  GE_CUDA(cudaEventCreate(&e0));
+  GE_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    GE_CUDA(cudaEventRecord(e0, ctx->stream));
+    k_fma_peak<T><<<ctas, threads, 0, ctx->stream>>>(out.get(), iters, (T)0.999999, (T)1e-6);
+    GE_CUDA(cudaEventRecord(e1, ctx->stream));
+    GE_CUDA(cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    GE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * iters * double(threads) * ctas;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
 
 int onchip_threshold() {
   const char* v = std::getenv("GE_ONCHIP_MAX");
@@ -323,6 +419,12 @@ ge_status ge_context_create(int device, void* cuda_stream, ge_context** out) {
                 "; this build contains sm_100a code only");
       throw Fail{GE_ERR_NO_DEVICE};
     }
+    {  // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+      cudaMemPool_t pool;
+      GE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+      uint64_t keep = UINT64_MAX;
+      GE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (cuda_stream) {
@@ -342,6 +444,17 @@ void ge_context_destroy(ge_context* ctx) {
 }
 
 int64_t ge_context_launch_count(const ge_context* ctx) { return ctx ? ctx->launches : 0; }
+void ge_context_bytes(const ge_context* ctx, double* h2d, double* d2h) {
+  if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0.0;
+  if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0.0;
+}
+ge_status ge_measure_fma_peak(ge_context* ctx, int precision, double* tflops) {
+  return guarded([&] {
+    require_ctx(ctx);
+    GE_REQUIRE(tflops != nullptr, "tflops is null");
+    *tflops = precision == GE_F32 ? fma_peak<float>(ctx) : fma_peak<double>(ctx);
+  });
+}
 
 ge_status ge_flat_forceatlas(ge_context* ctx, const ge_csr* A, int dim, double* coords,
                              const ge_params* p) {
@@ -508,6 +621,7 @@ ge_status ge_flat_plan_iterate(ge_flat_plan* plan, int iters) {
 ge_status ge_flat_plan_sync(ge_flat_plan* plan) {
   return guarded([&] { GE_CUDA(cudaStreamSynchronize(plan->solver->ctx->stream)); });
 }
+void ge_flat_plan_select_kernels(ge_flat_plan* plan, int mask) { plan->solver->select_kernels(mask); }
 void ge_flat_plan_profile(ge_flat_plan* plan, int enable) { plan->solver->profile(enable != 0); }
 ge_status ge_flat_plan_profile_get(ge_flat_plan* plan, double* repulsion_ms, int64_t* repulsion_launches,
                                    double* attract_step_ms, int64_t* attract_step_launches) {

@@ -72,6 +72,48 @@ struct Real<double> {
     const double w = fma(e, fma(e, c1875, c15), c);
     return q3 * w;
   }
+  // The same for N independent pairs against one column, stage by stage (instruction-level
+  // parallelism across the pairs hides the FP64 pipe latency).
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_mass_n(const double (&r2)[N], double c, double c15,
+                                                         double c1875, double (&s)[N]) {
+    double q[N], q2[N], e[N], w[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) e[t] = fma(-r2[t], q2[t], 1.0);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q2[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], c1875, c15);
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], w[t], c);
+#pragma unroll
+    for (int t = 0; t < N; ++t) s[t] = q2[t] * w[t];
+  }
+  // N independent pairs against N different columns.
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_mass_v(const double (&r2)[N], const double (&c)[N],
+                                                         const double (&c15)[N],
+                                                         const double (&c1875)[N], double (&s)[N]) {
+    double q[N], q2[N], e[N], w[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) e[t] = fma(-r2[t], q2[t], 1.0);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q2[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], c1875[t], c15[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], w[t], c[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) s[t] = q2[t] * w[t];
+  }
   // 1/sqrt(x) to ~1e-16: q (1-e)^(-1/2) = q (1 + e/2 + 3/8 e^2 + O(e^3)).  x = 0 -> NaN (callers
   // that can see zero guard it); 5 FP64-pipe instructions instead of CUDA's sqrt/div sequences.
   __device__ __forceinline__ static double rsqrt_acc(double x) {
@@ -103,6 +145,25 @@ struct Real<float> {
   __device__ __forceinline__ static float inv_cube_mass(float r2, float c, float, float) {
     const float q = rsqrt_seed(r2);
     return (q * q) * (q * c);
+  }
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_mass_n(const float (&r2)[N], float c, float, float,
+                                                         float (&s)[N]) {
+    float q[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) s[t] = (q[t] * q[t]) * (q[t] * c);
+  }
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_mass_v(const float (&r2)[N], const float (&c)[N],
+                                                         const float (&)[N], const float (&)[N],
+                                                         float (&s)[N]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+      const float q = rsqrt_seed(r2[t]);
+      s[t] = (q * q) * (q * c[t]);
+    }
   }
   __device__ __forceinline__ static float rsqrt_acc(float x) {
     const float q = rsqrt_seed(x);
@@ -150,9 +211,10 @@ inline Physics<T> make_physics(const ge_params& p) {
 // Attraction term factor g such that  force += (xj - xi) * g   (include/forceatlas.hpp:171-202).
 // With the defaults (linlog=false, delta=1, nohubs=false) the clamped distance cancels:
 //   direction * Fa = (xj-xi)/dis * attract * dis * a  =  (xj-xi) * attract * a.
-template <typename T>
+// GA = false compiles only the default path (no log / pow code in the hot kernels' loop bodies).
+template <typename T, bool GA = true>
 __device__ __forceinline__ T attraction_factor(T r2, T a, T deg_ip1, const Physics<T>& ph) {
-  if (!ph.general_attraction) return ph.attract * a;
+  if (!GA || !ph.general_attraction) return ph.attract * a;
   T dis = Real<T>::sqrt_(r2);
   if (dis < ph.eps) dis = ph.eps;
   T fa = dis;

@@ -29,33 +29,38 @@ inline double now_ms() {
       .count();
 }
 
-// Owning device allocation (cudaMalloc / cudaFree); movable, not copyable.
+// Owning device allocation from the stream-ordered memory pool of the context's device
+// (cudaMallocAsync / cudaFreeAsync on the context stream; the pool's release threshold is raised at
+// context creation so that repeated solves reuse memory instead of paying cudaMalloc / cudaFree,
+// which cost milliseconds and synchronise the device).  Movable, not copyable.
 template <typename T>
 class DevBuf {
  public:
   DevBuf() = default;
-  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(ge_context* ctx, size_t n) { alloc(ctx, n); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_), stream_(o.stream_) { o.p_ = nullptr; o.n_ = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
       release();
       p_ = o.p_;
       n_ = o.n_;
+      stream_ = o.stream_;
       o.p_ = nullptr;
       o.n_ = 0;
     }
     return *this;
   }
   ~DevBuf() { release(); }
-  void alloc(size_t n) {
+  void alloc(ge_context* ctx, size_t n) {
     release();
     n_ = n;
-    if (n) GE_CUDA(cudaMalloc(&p_, n * sizeof(T)));
+    stream_ = ctx->stream;
+    if (n) GE_CUDA(cudaMallocAsync(&p_, n * sizeof(T), stream_));
   }
   void release() {
-    if (p_) cudaFree(p_);
+    if (p_) cudaFreeAsync(p_, stream_);
     p_ = nullptr;
     n_ = 0;
   }
@@ -76,6 +81,7 @@ class DevBuf {
  private:
   T* p_ = nullptr;
   size_t n_ = 0;
+  cudaStream_t stream_ = nullptr;
 };
 
 // ---- ge_flat.cu ------------------------------------------------------------------------------
@@ -94,6 +100,7 @@ class FlatSolver {
   virtual void launch_iteration(bool update) = 0;
   virtual void swap() = 0;
   virtual void normalize() = 0;  // include/forceatlas.hpp:272-303 (single rank)
+  virtual void select_kernels(int mask) = 0;
   virtual void profile(bool enable) = 0;
   virtual void profile_get(double* rep_ms, int64_t* rep_n, double* step_ms, int64_t* step_n) = 0;
   ge_context* ctx = nullptr;
@@ -103,6 +110,7 @@ FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge
 
 // ---- ge_onchip.cu ----------------------------------------------------------------------------
 // Small flat solve entirely inside one CTA (coarsest level: n ~ 30-100, 100 000 iterations).
+constexpr int kOnchipMaxThreads = 1024;
 constexpr int kOnchipMaxVertices = 1024;
 void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
                        double* coords /* n x dim in/out */, double* forces_out /* or null */,

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <vector>
 
 #include "ge_flat.cuh"
@@ -77,8 +78,12 @@ struct VecLoad<float, 4> {
 };
 
 // K1a.  Each thread owns IPT rows (positions and force accumulators in registers); the CTA walks
-// its column range tile by tile.  Thread 0 is the TMA producer; everybody consumes through
-// broadcast shared-memory loads (all lanes read the same column -> conflict free).
+// column tiles.  Thread 0 is the TMA producer; everybody consumes through broadcast shared-memory
+// loads (all lanes read the same column -> conflict free).  Work = the flat sequence of
+// (row block, column tile) units, cut into gridDim.x equal contiguous shares: a CTA finishes the
+// tail of one row block, sweeps whole row blocks, and starts the head of another.  Whole blocks
+// are written straight to F; shared blocks go to the CTA's two partial slots and are summed in a
+// fixed order by k_repulsion_fixup (deterministic, no atomics).
 template <typename T, int D, int IPT>
 __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a) {
   constexpr int NM = Real<T>::kMassArrays;
@@ -89,20 +94,10 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
   T* tiles = reinterpret_cast<T*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kRepStages * kStageBytes);
 
-  const BlockDesc bd = a.blocks[blockIdx.x];
-  const int ntiles = (bd.j1 - bd.j0) / kTileJ;
   const int tid = threadIdx.x;
-
-  T xi[IPT][D], fi[IPT][D];
-#pragma unroll
-  for (int t = 0; t < IPT; ++t) {
-    const int i = bd.row0 + tid + t * blockDim.x;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      xi[t][k] = (i < bd.row1) ? a.pos[(int64_t)k * a.ld + i] : (T)0;
-      fi[t][k] = (T)0;
-    }
-  }
+  const long long W = a.total_units, G = gridDim.x, c = blockIdx.x;
+  const long long u0 = W * c / G, u1 = W * (c + 1) / G;
+  if (u0 >= u1) return;
 
   if (tid == 0) {
 #pragma unroll
@@ -111,67 +106,146 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
   }
   __syncthreads();
 
-  auto issue = [&](int tile) {
-    const int s = tile % kRepStages;
-    T* dst = tiles + (size_t)s * NA * kTileJ;
-    const int64_t j = (int64_t)bd.j0 + (int64_t)tile * kTileJ;
-    mbar_expect_tx(&full[s], kStageBytes);
-#pragma unroll
-    for (int k = 0; k < D; ++k)
-      tma_load_1d(dst + k * kTileJ, a.pos + (int64_t)k * a.ld + j, kTileJ * sizeof(T), &full[s]);
-#pragma unroll
-    for (int k = 0; k < NM; ++k)
-      tma_load_1d(dst + (D + k) * kTileJ, a.mass + (int64_t)k * a.ld + j, kTileJ * sizeof(T),
-                  &full[s]);
-  };
-
-  if (tid == 0) {
-    for (int t = 0; t < kRepStages - 1 && t < ntiles; ++t) issue(t);
+  // row block holding unit u0: last block with unit0 <= u0
+  int b = 0;
+  {
+    int lo = 0, hi = a.nblocks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (a.blocks[mid].unit0 <= u0) lo = mid;
+      else hi = mid - 1;
+    }
+    b = lo;
   }
 
-  for (int tile = 0; tile < ntiles; ++tile) {
-    __syncthreads();  // everyone is done with tile-1: its stage may be refilled
-    if (tid == 0 && tile + kRepStages - 1 < ntiles) issue(tile + kRepStages - 1);
-    const int s = tile % kRepStages;
-    mbar_wait(&full[s], (uint32_t)((tile / kRepStages) & 1));
-    const T* st = tiles + (size_t)s * NA * kTileJ;
+  long long u = u0;
+  unsigned g = 0;  // tiles this CTA has pushed through the pipeline (stage / parity bookkeeping)
+  while (u < u1) {
+    const BlockDesc bd = a.blocks[b];
+    const int t_begin = (int)(u - bd.unit0);
+    const int nt = (int)min((long long)(bd.ntiles - t_begin), u1 - u);
+
+    T xi[IPT][D], fi[IPT][D];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t) {
+      const int i = bd.row0 + tid + t * blockDim.x;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        xi[t][k] = (i < bd.row1) ? a.pos[(int64_t)k * a.ld + i] : (T)0;
+        fi[t][k] = (T)0;
+      }
+    }
+
+    auto issue = [&](int l) {  // l-th tile of this segment
+      const unsigned s = (g + (unsigned)l) % kRepStages;
+      T* dst = tiles + (size_t)s * NA * kTileJ;
+      const int64_t j = (int64_t)bd.j0 + (int64_t)(t_begin + l) * kTileJ;
+      mbar_expect_tx(&full[s], kStageBytes);
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+        tma_load_1d(dst + k * kTileJ, a.pos + (int64_t)k * a.ld + j, kTileJ * sizeof(T), &full[s]);
+#pragma unroll
+      for (int k = 0; k < NM; ++k)
+        tma_load_1d(dst + (D + k) * kTileJ, a.mass + (int64_t)k * a.ld + j, kTileJ * sizeof(T),
+                    &full[s]);
+    };
+    // The stages the prologue refills held tiles nt-3 / nt-2 of the previous segment, which every
+    // thread finished before the barrier of its last iteration.
+    if (tid == 0) {
+      for (int l = 0; l < kRepStages - 1 && l < nt; ++l) issue(l);
+    }
+
+    for (int l = 0; l < nt; ++l) {
+      __syncthreads();  // everyone is done with tile l-1: its stage may be refilled
+      if (tid == 0 && l + kRepStages - 1 < nt) issue(l + kRepStages - 1);
+      const unsigned gl = g + (unsigned)l;
+      const unsigned s = gl % kRepStages;
+      mbar_wait(&full[s], (gl / kRepStages) & 1u);
+      const T* st = tiles + (size_t)s * NA * kTileJ;
 
 #pragma unroll 1
-    for (int jj = 0; jj < kTileJ; jj += VEC) {
-      T xj[D][VEC], mj[3][VEC];
+      for (int jj = 0; jj < kTileJ; jj += VEC) {
+        T xj[D][VEC], mj[3][VEC];
 #pragma unroll
-      for (int k = 0; k < D; ++k) VecLoad<T, VEC>::ld(st + k * kTileJ + jj, xj[k]);
+        for (int k = 0; k < D; ++k) VecLoad<T, VEC>::ld(st + k * kTileJ + jj, xj[k]);
 #pragma unroll
-      for (int k = 0; k < NM; ++k) VecLoad<T, VEC>::ld(st + (D + k) * kTileJ + jj, mj[k]);
+        for (int k = 0; k < NM; ++k) VecLoad<T, VEC>::ld(st + (D + k) * kTileJ + jj, mj[k]);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
+        for (int v = 0; v < VEC; ++v) {
+          // The IPT pairs of one column are independent: written stage by stage so that the
+          // dependent FP chain of one pair is interleaved with the other pairs' (ILP = IPT).
+          T d[IPT][D], r2[IPT], s3[IPT];
 #pragma unroll
-        for (int t = 0; t < IPT; ++t) {
-          T d[D];
-          T r2 = (T)0;
+          for (int t = 0; t < IPT; ++t) {
+            r2[t] = (T)0;
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            d[k] = xi[t][k] - xj[k][v];
-            r2 = fma(d[k], d[k], r2);
+            for (int k = 0; k < D; ++k) {
+              d[t][k] = xi[t][k] - xj[k][v];
+              r2[t] = fma(d[t][k], d[t][k], r2[t]);
+            }
+            r2[t] = Real<T>::clamp_lo(r2[t], a.eps2);
           }
-          r2 = Real<T>::clamp_lo(r2, a.eps2);
-          const T s3 = Real<T>::inv_cube_mass(r2, mj[0][v], mj[NM > 1 ? 1 : 0][v],
-                                              mj[NM > 2 ? 2 : 0][v]);
+          Real<T>::template inv_cube_mass_n<IPT>(r2, mj[0][v], mj[NM > 1 ? 1 : 0][v],
+                                                 mj[NM > 2 ? 2 : 0][v], s3);
 #pragma unroll
-          for (int k = 0; k < D; ++k) fi[t][k] = fma(d[k], s3, fi[t][k]);
+          for (int t = 0; t < IPT; ++t) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) fi[t][k] = fma(d[t][k], s3[t], fi[t][k]);
+          }
         }
       }
     }
-  }
+    g += (unsigned)nt;
 
+    const bool whole = (t_begin == 0 && nt == bd.ntiles);
+    const int slot = (u == u0) ? 0 : 1;
 #pragma unroll
-  for (int t = 0; t < IPT; ++t) {
-    const int i = bd.row0 + tid + t * blockDim.x;
-    if (i < bd.row1) {
-      const T ci = a.mass[i] * a.repel;  // (deg_i + 1) * repel hoisted out of the pair loop
+    for (int t = 0; t < IPT; ++t) {
+      const int r = tid + t * blockDim.x;
+      const int i = bd.row0 + r;
+      if (i < bd.row1) {
+        if (whole) {
+          const T ci = a.mass[i] * a.repel;  // (deg_i + 1) * repel hoisted out of the pair loop
 #pragma unroll
-      for (int k = 0; k < D; ++k) a.F[(int64_t)k * a.ldf + (i - a.f_row_base)] = fi[t][k] * ci;
+          for (int k = 0; k < D; ++k) a.F[(int64_t)k * a.ldf + (i - a.f_row_base)] = fi[t][k] * ci;
+        } else {
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            a.partial[(((size_t)c * 2 + slot) * D + k) * a.rows_per_block + r] = fi[t][k];
+        }
+      }
     }
+    u += nt;
+    ++b;
+  }
+}
+
+// Sums, in CTA order, the partial results of the row blocks that k_repulsion split between CTAs.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_repulsion_fixup(const RepArgs<T> a, int grid) {
+  const BlockDesc bd = a.blocks[blockIdx.x];
+  const long long W = a.total_units, G = grid;
+  const long long U0 = bd.unit0, U1 = bd.unit0 + bd.ntiles;
+  long long c = U0 * G / W;
+  while (c + 1 < G && W * (c + 1) / G <= U0) ++c;
+  while (c > 0 && W * c / G > U0) --c;
+  if (W * c / G <= U0 && W * (c + 1) / G >= U1) return;  // swept whole by one CTA
+  for (int r = threadIdx.x; bd.row0 + r < bd.row1; r += blockDim.x) {
+    T acc[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = (T)0;
+    for (long long cc = c; cc < G && W * cc / G < U1; ++cc) {
+      const long long v0 = W * cc / G, v1 = W * (cc + 1) / G;
+      if (v1 <= U0 || v0 >= v1) continue;
+      const int slot = (max(v0, U0) == v0) ? 0 : 1;
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+        acc[k] += a.partial[(((size_t)cc * 2 + slot) * D + k) * a.rows_per_block + r];
+    }
+    const int i = bd.row0 + r;
+    const T ci = a.mass[i] * a.repel;
+#pragma unroll
+    for (int k = 0; k < D; ++k) a.F[(int64_t)k * a.ldf + (i - a.f_row_base)] = acc[k] * ci;
   }
 }
 
@@ -179,50 +253,62 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
 // group finishes the row: adds the repulsion sum, gravity, derives the per-vertex speed and
 // writes the moved position into the NEXT coordinate buffer (Jacobi: everybody still reads the
 // current one).
-template <typename T, int D, int G, bool ML>
-__global__ void __launch_bounds__(256) k_attract_step(const StepArgs<T> a) {
+template <typename T, int D, int G, bool ML, bool GA>
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(const StepArgs<T> a) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gtid / G;
   const int lane = gtid % G;
   const bool active = r < a.nrows;
   const int i = a.row0 + (active ? r : 0);
-  T x[D], f[D];
+  // Issue every load whose address is known up front before walking the row, so the row's
+  // index -> coordinate gather chain overlaps them (the kernel is latency-, not issue-bound).
+  const int e0 = active ? a.e_begin[r] : 0;
+  const int e1 = active ? a.e_end[r] : 0;
+  T x[D], f[D], frep[D], fprev[D], E[D];
+  const bool finisher = active && lane == 0;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     x[k] = a.pos_cur[(int64_t)k * a.ld + i];
     f[k] = (T)0;
+    frep[k] = finisher ? a.Frep[(int64_t)k * a.ldf + r] : (T)0;
+    fprev[k] = (finisher && a.update) ? a.Fprev[(int64_t)k * a.ldf + r] : (T)0;
+    E[k] = (ML && finisher && a.Eext != nullptr) ? a.Eext[(int64_t)k * a.ldf + r] : (T)0;
   }
   const T ci = a.mass[i];
-  if (active) {
-    const int e1 = a.e_end[r];
-    for (int e = a.e_begin[r] + lane; e < e1; e += G) {
-      const int j = a.J[e];
-      const T w = (a.W != nullptr && a.ph.use_weights) ? a.W[e] : (T)1;
-      T d[D];
-      T r2 = (T)0;
+  const bool weighted = a.W != nullptr && a.ph.use_weights;
+  // two entries per lane and trip: both index loads, then both gathers, are in flight together
+  for (int e = e0 + lane; e < e1; e += 2 * G) {
+    const int eb = e + G;
+    const bool two = eb < e1;
+    const int ja = a.J[e];
+    const int jb = two ? a.J[eb] : ja;
+    const T wa = weighted ? a.W[e] : (T)1;
+    const T wb = (weighted && two) ? a.W[eb] : (T)1;
+    T da[D], db[D];
+    T r2a = (T)0, r2b = (T)0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        d[k] = a.pos_cur[(int64_t)k * a.ld + j] - x[k];
-        r2 = fma(d[k], d[k], r2);
-      }
-      const T g = attraction_factor<T>(r2, w, ci, a.ph);
-#pragma unroll
-      for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+    for (int k = 0; k < D; ++k) {
+      da[k] = a.pos_cur[(int64_t)k * a.ld + ja] - x[k];
+      db[k] = a.pos_cur[(int64_t)k * a.ld + jb] - x[k];
     }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      r2a = fma(da[k], da[k], r2a);
+      r2b = fma(db[k], db[k], r2b);
+    }
+    const T ga = attraction_factor<T, GA>(r2a, wa, ci, a.ph);
+    const T gb = two ? attraction_factor<T, GA>(r2b, wb, ci, a.ph) : (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = fma(db[k], gb, fma(da[k], ga, f[k]));
   }
 #pragma unroll
   for (int off = G / 2; off > 0; off >>= 1) {
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off, G);
   }
-  if (active && lane == 0) {
-    T fprev[D], E[D];
+  if (finisher) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      f[k] += a.Frep[(int64_t)k * a.ldf + r];
-      fprev[k] = a.update ? a.Fprev[(int64_t)k * a.ldf + r] : (T)0;
-      E[k] = (ML && a.Eext != nullptr) ? a.Eext[(int64_t)k * a.ldf + r] : (T)0;
-    }
+    for (int k = 0; k < D; ++k) f[k] += frep[k];
     vertex_step<T, D, ML>(x, f, fprev, E, ci, a.ph);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -317,6 +403,12 @@ __global__ void __launch_bounds__(1024) k_normalize(T* pos, int n, int64_t ld) {
 // ---------------------------------------------------------------------------------------------
 // launchers (also used by ge_multilevel.cu for aggregates too large for one CTA)
 // ---------------------------------------------------------------------------------------------
+namespace {
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
 template <typename T>
 size_t repulsion_smem(int dim) {
   return (size_t)kRepStages * (dim + Real<T>::kMassArrays) * kTileJ * sizeof(T) +
@@ -331,30 +423,94 @@ const void* repulsion_kernel(int dim, int ipt) {
   return ipt == 1 ? (const void*)k_repulsion<T, 3, 1>
                   : ipt == 2 ? (const void*)k_repulsion<T, 3, 2> : (const void*)k_repulsion<T, 3, 4>;
 }
+}  // namespace
 
 template <typename T>
-void launch_repulsion(ge_context* ctx, const RepArgs<T>& a, int nblocks, int threads, int ipt,
-                      int dim) {
-  if (nblocks == 0) return;
-  const void* fn = repulsion_kernel<T>(dim, ipt);
-  const size_t smem = repulsion_smem<T>(dim);
+RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowSegment>& segments)
+    : ctx_(ctx), dim_(dim) {
+  // Launch shape measured on B200 (tools/sweep_rep.py): 512 threads, 2 rows per thread in FP64
+  // (56-64 registers -> 2 CTAs = 32 warps per SM), 4 rows per thread in FP32.  Small sweeps use
+  // narrower CTAs so that there are enough (row block, tile) units to share out.
+  long long total_rows = 0;
+  for (const auto& sg : segments) total_rows += sg.row1 - sg.row0;
+  ipt_ = env_int("GE_REP_IPT", sizeof(T) == 8 ? 2 : 4);
+  threads_ = env_int("GE_REP_THREADS", 512);
+  while (threads_ > 128 && total_rows < (long long)ctx->sm_count * threads_ * ipt_) threads_ /= 2;
+  const void* fn = repulsion_kernel<T>(dim_, ipt_);
+  const size_t smem = repulsion_smem<T>(dim_);
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = {(void*)&a};
-  GE_CUDA(cudaLaunchKernel(fn, dim3(nblocks), dim3(threads), args, smem, ctx->stream));
-  ctx->launches++;
+  int occ = 0;
+  GE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads_, smem));
+  GE_REQUIRE(occ > 0, "repulsion kernel does not fit on an SM");
+  const int rows_per_block = threads_ * ipt_;
+  std::vector<BlockDesc> blocks;
+  long long units = 0;
+  for (const auto& sg : segments) {
+    const int ntiles = (sg.j1 - sg.j0) / kTileJ;
+    for (int r = sg.row0; r < sg.row1; r += rows_per_block) {
+      blocks.push_back(BlockDesc{r, std::min(sg.row1, r + rows_per_block), sg.j0, ntiles, units});
+      units += ntiles;
+    }
+  }
+  nblocks_ = (int)blocks.size();
+  total_units_ = units;
+  grid_ = (int)std::min<long long>((long long)ctx->sm_count * occ, std::max<long long>(units, 1));
+  blocks_.alloc(ctx, std::max<size_t>(blocks.size(), 1));
+  blocks_.upload(ctx, blocks.data(), blocks.size());
+  partial_.alloc(ctx, (size_t)grid_ * 2 * dim_ * rows_per_block);
+  GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (std::getenv("GE_VERBOSE"))
+    std::fprintf(stderr, "[ge] repulsion plan: threads=%d ipt=%d grid=%d (occ %d) blocks=%d units=%lld\n",
+                 threads_, ipt_, grid_, occ, nblocks_, total_units_);
 }
 
+template <typename T>
+void RepulsionPlan<T>::launch(const T* pos, const T* mass, int64_t ld, T* F, int64_t ldf,
+                              int f_row_base, T repel, T eps2) {
+  if (nblocks_ == 0 || total_units_ == 0) return;
+  RepArgs<T> a;
+  a.pos = pos;
+  a.mass = mass;
+  a.F = F;
+  a.partial = partial_.get();
+  a.blocks = blocks_.get();
+  a.ld = ld;
+  a.ldf = ldf;
+  a.total_units = total_units_;
+  a.nblocks = nblocks_;
+  a.rows_per_block = threads_ * ipt_;
+  a.f_row_base = f_row_base;
+  a.repel = repel;
+  a.eps2 = eps2;
+  void* args[] = {(void*)&a};
+  GE_CUDA(cudaLaunchKernel(repulsion_kernel<T>(dim_, ipt_), dim3(grid_), dim3(threads_), args,
+                           repulsion_smem<T>(dim_), ctx_->stream));
+  ctx_->launches++;
+  if (dim_ == 2) k_repulsion_fixup<T, 2><<<nblocks_, 256, 0, ctx_->stream>>>(a, grid_);
+  else k_repulsion_fixup<T, 3><<<nblocks_, 256, 0, ctx_->stream>>>(a, grid_);
+  GE_CUDA(cudaGetLastError());
+  ctx_->launches++;
+}
+
+template class RepulsionPlan<double>;
+template class RepulsionPlan<float>;
+
 namespace {
-template <typename T, int D, bool ML>
+template <typename T, int D, bool ML, bool GA>
 void launch_step_g(ge_context* ctx, const StepArgs<T>& a, int group) {
   const int g = group <= 4 ? 4 : group <= 8 ? 8 : group <= 16 ? 16 : 32;
   const int64_t threads = (int64_t)a.nrows * g;
   const unsigned grid = (unsigned)((threads + 255) / 256);
-  if (g == 4) k_attract_step<T, D, 4, ML><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (g == 8) k_attract_step<T, D, 8, ML><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (g == 16) k_attract_step<T, D, 16, ML><<<grid, 256, 0, ctx->stream>>>(a);
-  else k_attract_step<T, D, 32, ML><<<grid, 256, 0, ctx->stream>>>(a);
+  if (g == 4) k_attract_step<T, D, 4, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (g == 8) k_attract_step<T, D, 8, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (g == 16) k_attract_step<T, D, 16, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  else k_attract_step<T, D, 32, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+}
+template <typename T, int D, bool ML>
+void launch_step_ga(ge_context* ctx, const StepArgs<T>& a, int group) {
+  if (a.ph.general_attraction) launch_step_g<T, D, ML, true>(ctx, a, group);
+  else launch_step_g<T, D, ML, false>(ctx, a, group);
 }
 }  // namespace
 
@@ -362,22 +518,16 @@ template <typename T>
 void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int group, bool ml) {
   if (a.nrows == 0) return;
   if (dim == 2) {
-    if (ml) launch_step_g<T, 2, true>(ctx, a, group);
-    else launch_step_g<T, 2, false>(ctx, a, group);
+    if (ml) launch_step_ga<T, 2, true>(ctx, a, group);
+    else launch_step_ga<T, 2, false>(ctx, a, group);
   } else {
-    if (ml) launch_step_g<T, 3, true>(ctx, a, group);
-    else launch_step_g<T, 3, false>(ctx, a, group);
+    if (ml) launch_step_ga<T, 3, true>(ctx, a, group);
+    else launch_step_ga<T, 3, false>(ctx, a, group);
   }
   GE_CUDA(cudaGetLastError());
   ctx->launches++;
 }
 
-template size_t repulsion_smem<double>(int);
-template size_t repulsion_smem<float>(int);
-template const void* repulsion_kernel<double>(int, int);
-template const void* repulsion_kernel<float>(int, int);
-template void launch_repulsion<double>(ge_context*, const RepArgs<double>&, int, int, int, int);
-template void launch_repulsion<float>(ge_context*, const RepArgs<float>&, int, int, int, int);
 template void launch_attract_step<double>(ge_context*, const StepArgs<double>&, int, int, bool);
 template void launch_attract_step<float>(ge_context*, const StepArgs<float>&, int, int, bool);
 
@@ -389,11 +539,6 @@ int group_for_degree(double avg_deg) {
 // device-resident flat solver
 // ---------------------------------------------------------------------------------------------
 namespace {
-
-int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
-}
 
 template <typename T>
 class FlatSolverT final : public FlatSolver {
@@ -420,9 +565,9 @@ class FlatSolverT final : public FlatSolver {
       }
       deg[i] = s;
     }
-    DevBuf<double> d_deg(std::max(n_, 1));
+    DevBuf<double> d_deg(ctx, std::max(n_, 1));
     d_deg.upload(ctx, deg.data(), n_);
-    mass_.alloc((size_t)NM * ld_);
+    mass_.alloc(ctx, (size_t)NM * ld_);
     k_mass_from_degree<T><<<(unsigned)((ld_ + 255) / 256), 256, 0, ctx->stream>>>(
         d_deg.get(), n_, ld_, NM, mass_.get());
     ctx->launches++;
@@ -432,32 +577,32 @@ class FlatSolverT final : public FlatSolver {
     const int lnnz = e1 - e0;
     std::vector<int> rowptr(nrows_ + 1);
     for (int r = 0; r <= nrows_; ++r) rowptr[r] = A.indptr[rb_ + r] - e0;
-    rowptr_.alloc(nrows_ + 1);
+    rowptr_.alloc(ctx, nrows_ + 1);
     rowptr_.upload(ctx, rowptr.data(), nrows_ + 1);
-    J_.alloc(std::max(lnnz, 1));
+    J_.alloc(ctx, std::max(lnnz, 1));
     J_.upload(ctx, A.indices + e0, lnnz);
     std::vector<T> w;
     if (weighted) {
       w.resize(lnnz);
       for (int e = 0; e < lnnz; ++e) w[e] = (T)A.data[e0 + e];
-      W_.alloc(std::max(lnnz, 1));
+      W_.alloc(ctx, std::max(lnnz, 1));
       W_.upload(ctx, w.data(), lnnz);
     }
     avg_deg_ = nrows_ > 0 ? double(lnnz) / nrows_ : 0.0;
 
-    own0_.alloc((size_t)dim_ * ld_);
-    own1_.alloc((size_t)dim_ * ld_);
+    own0_.alloc(ctx, (size_t)dim_ * ld_);
+    own1_.alloc(ctx, (size_t)dim_ * ld_);
     own0_.zero(ctx->stream);
     own1_.zero(ctx->stream);
     buf_[0] = own0_.get();
     buf_[1] = own1_.get();
-    Frep_.alloc((size_t)dim_ * ldf_);
-    Fprev_.alloc((size_t)dim_ * ldf_);
+    Frep_.alloc(ctx, (size_t)dim_ * ldf_);
+    Fprev_.alloc(ctx, (size_t)dim_ * ldf_);
     Frep_.zero(ctx->stream);
     Fprev_.zero(ctx->stream);
-    stage_.alloc((size_t)std::max(n_, 1) * dim_);
+    stage_.alloc(ctx, (size_t)std::max(n_, 1) * dim_);
 
-    plan_repulsion();
+    rep_.reset(new RepulsionPlan<T>(ctx, dim_, {RowSegment{rb_, re_, 0, (int)ld_}}));
     for (auto& e : ev_) GE_CUDA(cudaEventCreate(&e));
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -511,17 +656,8 @@ class FlatSolverT final : public FlatSolver {
   void launch_iteration(bool update) override {
     if (nrows_ == 0) return;
     if (prof_) GE_CUDA(cudaEventRecord(ev_[0], ctx->stream));
-    RepArgs<T> ra;
-    ra.pos = buf_[cur_];
-    ra.mass = mass_.get();
-    ra.F = Frep_.get();
-    ra.blocks = blocks_.get();
-    ra.ld = ld_;
-    ra.ldf = ldf_;
-    ra.f_row_base = rb_;
-    ra.repel = ph_.repel;
-    ra.eps2 = ph_.eps2;
-    launch_repulsion<T>(ctx, ra, rep_blocks_n_, rep_threads_, rep_ipt_, dim_);
+    if (kernel_mask_ & 1)
+      rep_->launch(buf_[cur_], mass_.get(), ld_, Frep_.get(), ldf_, rb_, ph_.repel, ph_.eps2);
     if (prof_) GE_CUDA(cudaEventRecord(ev_[1], ctx->stream));
     StepArgs<T> sa;
     sa.e_begin = rowptr_.get();
@@ -540,7 +676,8 @@ class FlatSolverT final : public FlatSolver {
     sa.nrows = nrows_;
     sa.update = update ? 1 : 0;
     sa.ph = ph_;
-    launch_attract_step<T>(ctx, sa, dim_, env_int("GE_STEP_GROUP", group_for_degree(avg_deg_)), false);
+    if (kernel_mask_ & 2)
+      launch_attract_step<T>(ctx, sa, dim_, env_int("GE_STEP_GROUP", group_for_degree(avg_deg_)), false);
     if (prof_) {
       GE_CUDA(cudaEventRecord(ev_[2], ctx->stream));
       GE_CUDA(cudaEventSynchronize(ev_[2]));
@@ -562,6 +699,7 @@ class FlatSolverT final : public FlatSolver {
     ctx->launches++;
     GE_CUDA(cudaGetLastError());
   }
+  void select_kernels(int mask) override { kernel_mask_ = mask; }
   void profile(bool enable) override {
     prof_ = enable;
     rep_ms_ = step_ms_ = 0;
@@ -575,75 +713,18 @@ class FlatSolverT final : public FlatSolver {
   }
 
  private:
-  // Choose threads-per-CTA and rows-per-thread so that the grid fills whole waves of the
-  // 148 SMs x resident CTAs; overridable with GE_REP_THREADS / GE_REP_IPT for sweeps.
-  void plan_repulsion() {
-    const int sms = ctx->sm_count;
-    double best_score = -1.0;
-    const int force_thr = env_int("GE_REP_THREADS", 0), force_ipt = env_int("GE_REP_IPT", 0);
-    const size_t smem = repulsion_smem<T>(dim_);
-    for (int ipt : {4, 2, 1}) {
-      if (force_ipt && ipt != force_ipt) continue;
-      const void* fn = repulsion_kernel<T>(dim_, ipt);
-      for (int thr = 128; thr <= kRepMaxThreads; thr += 32) {
-        if (force_thr && thr != force_thr) continue;
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, thr, smem) != cudaSuccess ||
-            occ == 0) {
-          cudaGetLastError();
-          continue;
-        }
-        const int64_t rows_per_cta = (int64_t)thr * ipt;
-        const int64_t ctas = (nrows_ + rows_per_cta - 1) / rows_per_cta;
-        const int64_t slots = (int64_t)sms * occ;
-        const int64_t waves = (ctas + slots - 1) / slots;
-        // useful row-slots / row-slots paid for ...
-        double score;
-        if (waves == 1) {
-          const int64_t per_sm = (ctas + sms - 1) / sms;  // CTAs on the busiest SM
-          score = double(nrows_) / double(per_sm * sms * rows_per_cta);
-        } else {
-          score = double(nrows_) / double(waves * slots * rows_per_cta);
-        }
-        // ... times a mild preference for register blocking (fewer shared-memory reads per
-        // pair) and for at least 8 resident warps per SM (latency hiding on the FP64 pipe).
-        const int res_ctas = (int)std::min<int64_t>(occ, (ctas + sms - 1) / sms);
-        const double warps = double(res_ctas) * thr / 32.0;
-        score *= (ipt == 4 ? 1.0 : ipt == 2 ? 0.97 : 0.90);
-        score *= std::min(1.0, 0.6 + 0.05 * warps);
-        if (score > best_score) {
-          best_score = score;
-          rep_threads_ = thr;
-          rep_ipt_ = ipt;
-        }
-      }
-    }
-    GE_REQUIRE(best_score > 0, "no launchable repulsion configuration");
-    const int rows_per_cta = rep_threads_ * rep_ipt_;
-    std::vector<BlockDesc> blocks;
-    for (int r = rb_; r < re_; r += rows_per_cta)
-      blocks.push_back(BlockDesc{r, std::min(re_, r + rows_per_cta), 0, (int)ld_});
-    rep_blocks_n_ = (int)blocks.size();
-    blocks_.alloc(std::max<size_t>(blocks.size(), 1));
-    blocks_.upload(ctx, blocks.data(), blocks.size());
-    GE_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (std::getenv("GE_VERBOSE"))
-      std::fprintf(stderr, "[ge] repulsion plan: threads=%d ipt=%d ctas=%d smem=%zu\n", rep_threads_,
-                   rep_ipt_, rep_blocks_n_, smem);
-  }
-
   int n_, dim_, rb_, re_, nrows_ = 0;
   int64_t ld_ = 0, ldf_ = 0;
   Physics<T> ph_;
   double avg_deg_ = 0;
   DevBuf<T> mass_, own0_, own1_, Frep_, Fprev_, W_;
   DevBuf<int> rowptr_, J_;
-  DevBuf<BlockDesc> blocks_;
+  std::unique_ptr<RepulsionPlan<T>> rep_;
   DevBuf<double> stage_;
   T* buf_[2] = {nullptr, nullptr};
   int cur_ = 0;
-  int rep_threads_ = 256, rep_ipt_ = 4, rep_blocks_n_ = 0;
   bool prof_ = false;
+  int kernel_mask_ = 3;
   double rep_ms_ = 0, step_ms_ = 0;
   int64_t rep_n_ = 0, step_n_ = 0;
   cudaEvent_t ev_[3] = {nullptr, nullptr, nullptr};

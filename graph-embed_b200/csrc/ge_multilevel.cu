@@ -6,7 +6,7 @@
 // synchronisation.  Work is binned by aggregate size:
 //   1 member      k_ml_singletons : closed form (centre - mean = 0  =>  x = coords_A[a]).
 //   2..32         k_onchip_warp   : one lane per member, packs of equal-size aggregates per warp.
-//   33..cta_max   k_onchip_cta    : one CTA per aggregate, positions in shared memory.
+//   33..512       k_onchip_cta    : one CTA per aggregate, positions in shared memory.
 //   larger        k_repulsion / k_attract_step over 256-aligned segments, one launch pair per
 //                 iteration, then k_ml_segment_epilogue (R-MAT hierarchies: up to ~3800 members).
 // Vertices are renumbered into SLOTS so that each aggregate is contiguous (member order of the
@@ -253,7 +253,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   std::sort(cta_aggs.begin(), cta_aggs.end(), [&](int x, int y) { return size_of(x) > size_of(y); });
 
   std::vector<int> agg_base(std::max(m, 1), 0);
-  std::vector<int4> segs, cta_tasks, packs;
+  std::vector<int4> segs, packs;
   int64_t cursor = 0;
   for (int a : grid_aggs) {
     const int s = size_of(a);
@@ -262,15 +262,24 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     cursor = round_up(cursor + s, kTileJ);
   }
   const int grid_slots = (int)cursor;
-  int cta_threads = 32, cta_size_max = 1;
+  // CTA tier: one launch per lanes-per-vertex class (the kernel is specialised on it)
+  struct CtaClass {
+    std::vector<int4> tasks;
+    int threads = 32, size_max = 1;
+  };
+  CtaClass cta_class[6];  // L = 1, 2, 4, 8, 16, 32
   for (int a : cta_aggs) {
     const int s = size_of(a);
     agg_base[a] = (int)cursor;
-    int L = 1;
-    while (L < 32 && (int64_t)s * (L * 2) <= 1024) L *= 2;
-    cta_tasks.push_back(make_int4((int)cursor, s, a, L));
-    cta_threads = std::max<int>(cta_threads, (int)round_up((int64_t)s * L, 32));
-    cta_size_max = std::max(cta_size_max, s);
+    int L = 1, li = 0;
+    while (L < 8 && (int64_t)s * (L * 2) <= kOnchipMaxThreads) {
+      L *= 2;
+      ++li;
+    }
+    CtaClass& cc = cta_class[li];
+    cc.tasks.push_back(make_int4((int)cursor, s, a, L));
+    cc.threads = std::max<int>(cc.threads, (int)round_up((int64_t)s * L, 32));
+    cc.size_max = std::max(cc.size_max, s);
     cursor += s;
   }
   const int single_lo = forces_only ? 1 : 2;  // forces hook: singletons go through the warp tier
@@ -306,19 +315,16 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   }
 
   // ---- upload ------------------------------------------------------------------------------
-  DevBuf<int> d_I(n + 1), d_J(std::max(nnz, 1)), d_vA(std::max(n, 1)), d_vtx((size_t)ld),
-      d_slot_of(std::max(n, 1)), d_agg_base(std::max(m, 1)), d_agg_of_slot((size_t)ld),
-      d_eb((size_t)ld), d_ee((size_t)ld), d_eidx(std::max(nnz, 1));
-  DevBuf<double> d_Dw, d_cA((size_t)std::max(m, 1) * dim), d_rA(std::max(m, 1)),
-      d_init((size_t)std::max(n, 1) * dim), d_out((size_t)std::max(n, 1) * dim);
-  DevBuf<T> d_mass((size_t)NM * ld), d_E((size_t)dim * ld), d_ew;
+  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1)), d_vA(ctx, std::max(n, 1)), d_vtx(ctx, (size_t)ld), d_slot_of(ctx, std::max(n, 1)), d_agg_base(ctx, std::max(m, 1)), d_agg_of_slot(ctx, (size_t)ld), d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
+  DevBuf<double> d_Dw, d_cA(ctx, (size_t)std::max(m, 1) * dim), d_rA(ctx, std::max(m, 1)), d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
+  DevBuf<T> d_mass(ctx, (size_t)NM * ld), d_E(ctx, (size_t)dim * ld), d_ew;
   d_I.upload(ctx, A.indptr, n + 1);
   d_J.upload(ctx, A.indices, nnz);
   if (A.data != nullptr) {
-    d_Dw.alloc(std::max(nnz, 1));
+    d_Dw.alloc(ctx, std::max(nnz, 1));
     d_Dw.upload(ctx, A.data, nnz);
   }
-  if (weighted) d_ew.alloc(std::max(nnz, 1));
+  if (weighted) d_ew.alloc(ctx, std::max(nnz, 1));
   d_vA.upload(ctx, v_A, n);
   d_vtx.upload(ctx, vtx.data(), (size_t)ld);
   d_slot_of.upload(ctx, slot_of.data(), n);
@@ -392,8 +398,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   }
 
   // ---- warp tier ---------------------------------------------------------------------------
-  DevBuf<int4> d_packs(std::max<size_t>(packs.size(), 1)), d_tasks(std::max<size_t>(cta_tasks.size(), 1)),
-      d_segs(std::max<size_t>(segs.size(), 1));
+  DevBuf<int4> d_packs(ctx, std::max<size_t>(packs.size(), 1)), d_segs(ctx, std::max<size_t>(segs.size(), 1));
   if (!packs.empty()) {
     d_packs.upload(ctx, packs.data(), packs.size());
     OnchipArgs<T> wa = oa;
@@ -401,21 +406,24 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     launch_onchip_warp<T>(ctx, wa, (int)packs.size(), dim);
   }
   // ---- CTA tier ----------------------------------------------------------------------------
-  if (!cta_tasks.empty()) {
-    d_tasks.upload(ctx, cta_tasks.data(), cta_tasks.size());
+  std::vector<DevBuf<int4>> d_cta_tasks(6);
+  for (int li = 0; li < 6; ++li) {
+    CtaClass& cc = cta_class[li];
+    if (cc.tasks.empty()) continue;
+    d_cta_tasks[li].alloc(ctx, cc.tasks.size());
+    d_cta_tasks[li].upload(ctx, cc.tasks.data(), cc.tasks.size());
     OnchipArgs<T> ca = oa;
-    ca.tasks = d_tasks.get();
-    launch_onchip_cta<T>(ctx, ca, (int)cta_tasks.size(), dim, true, cta_threads, cta_size_max);
+    ca.tasks = d_cta_tasks[li].get();
+    launch_onchip_cta<T>(ctx, ca, (int)cc.tasks.size(), dim, true, 1 << li, cc.threads, cc.size_max);
   }
   // ---- grid tier ---------------------------------------------------------------------------
   DevBuf<T> d_pos0, d_pos1, d_Frep, d_Fprev;
-  DevBuf<BlockDesc> d_blocks;
   if (!segs.empty()) {
     d_segs.upload(ctx, segs.data(), segs.size());
-    d_pos0.alloc((size_t)dim * ld);
-    d_pos1.alloc((size_t)dim * ld);
-    d_Frep.alloc((size_t)dim * ld);
-    d_Fprev.alloc((size_t)dim * ld);
+    d_pos0.alloc(ctx, (size_t)dim * ld);
+    d_pos1.alloc(ctx, (size_t)dim * ld);
+    d_Frep.alloc(ctx, (size_t)dim * ld);
+    d_Fprev.alloc(ctx, (size_t)dim * ld);
     d_pos0.zero(ctx->stream);
     d_pos1.zero(ctx->stream);
     d_Frep.zero(ctx->stream);
@@ -425,35 +433,16 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     else k_ml_gather_pos<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_init.get(), d_vtx.get(), grid_slots, ld, d_pos0.get());
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
-    // row blocks: 128 threads x IPT rows, each against its own segment's 256-aligned column range
-    const int rep_threads = 128;
-    int64_t total_rows = 0;
-    for (auto& sg : segs) total_rows += sg.y;
-    const int ipt = total_rows >= (int64_t)ctx->sm_count * 2 * rep_threads * 2 ? 2 : 1;
-    std::vector<BlockDesc> blocks;
-    for (auto& sg : segs) {
-      const int j0 = sg.x, j1 = (int)round_up((int64_t)sg.x + sg.y, kTileJ);
-      for (int r = sg.x; r < sg.x + sg.y; r += rep_threads * ipt)
-        blocks.push_back(BlockDesc{r, std::min(sg.x + sg.y, r + rep_threads * ipt), j0, j1});
-    }
-    d_blocks.alloc(blocks.size());
-    d_blocks.upload(ctx, blocks.data(), blocks.size());
+    std::vector<RowSegment> rsegs;
+    for (auto& sg : segs)
+      rsegs.push_back(RowSegment{sg.x, sg.x + sg.y, sg.x, (int)round_up((int64_t)sg.x + sg.y, kTileJ)});
+    RepulsionPlan<T> rep(ctx, dim, rsegs);
     T* pos[2] = {d_pos0.get(), d_pos1.get()};
     int cur = 0;
     const int iters = forces_only ? 1 : p.iterations;
     const double avg_deg = grid_slots > 0 ? double(nnz) / std::max(n, 1) : 0.0;
     for (int it = 0; it < iters; ++it) {
-      RepArgs<T> ra;
-      ra.pos = pos[cur];
-      ra.mass = d_mass.get();
-      ra.F = d_Frep.get();
-      ra.blocks = d_blocks.get();
-      ra.ld = ld;
-      ra.ldf = ld;
-      ra.f_row_base = 0;
-      ra.repel = oa.ph.repel;
-      ra.eps2 = oa.ph.eps2;
-      launch_repulsion<T>(ctx, ra, (int)blocks.size(), rep_threads, ipt, dim);
+      rep.launch(pos[cur], d_mass.get(), ld, d_Frep.get(), ld, 0, oa.ph.repel, oa.ph.eps2);
       StepArgs<T> sa;
       sa.e_begin = d_eb.get();
       sa.e_end = d_ee.get();

@@ -14,6 +14,7 @@
 //                equal-size aggregates packed into one warp, __syncwarp instead of __syncthreads.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "ge_onchip.cuh"
@@ -22,26 +23,31 @@ namespace ge {
 
 namespace {
 
-template <typename T, int D, bool ML>
-__global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
+// BIG = false: up to 512 threads (128 registers each), U = 4 independent pairs per trip of the pair
+// loop (instruction-level parallelism); BIG = true: up to 1024 threads (64 registers), U = 2 and
+// twice the resident warps (thread-level parallelism) for the larger problems.
+// GA: general attraction (linlog / delta / nohubs) compiled in.
+template <typename T, int D, bool ML, int L, bool BIG, bool GA>
+__global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArgs<T> a) {
   constexpr int NM = Real<T>::kMassArrays;
+  constexpr int U = BIG ? 2 : 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
   __shared__ double bc[D + 1];
 
   const int4 task = a.tasks[blockIdx.x];
-  const int slot0 = task.x, s = task.y, agg = task.z, L = task.w;
+  const int slot0 = task.x, s = task.y, agg = task.z;
   const int S = (s + 1) & ~1;
   T* pos = reinterpret_cast<T*>(smem_raw);  // [2][D][S]
   T* ms = pos + 2 * D * S;                  // [NM][S]
 
   const int tid = threadIdx.x;
-  const int lshift = 31 - __clz(L);
-  const int lv = tid >> lshift;
-  const int part = tid & (L - 1);
+  const int lv = tid / L;
+  const int part = tid % L;
   const bool owner = lv < s;
   const int slot = slot0 + (owner ? lv : 0);
   const int v = a.vtx ? a.vtx[slot] : slot;
+  const Physics<T> ph = a.ph;  // registers, not constant-bank reloads inside the loop
 
   T x[D], fprev[D], E[D];
 #pragma unroll
@@ -51,9 +57,21 @@ __global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
     E[k] = (ML && a.Eext) ? a.Eext[(int64_t)k * a.ld + slot] : (T)0;
   }
   const T ci = a.mass[slot];
-  const T ci_repel = ci * a.ph.repel;
+  const T ci_repel = ci * ph.repel;
   const int eb = owner ? a.e_begin[slot] : 0;
   const int ee = owner ? a.e_end[slot] : 0;
+  // The first two attraction entries of this lane live in registers (coarse graphs have ~1-2
+  // entries per lane); longer rows continue from the compact list through L1.
+  int ej[2] = {0, 0};
+  T ew[2] = {(T)0, (T)0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int e = eb + part + q * L;
+    if (e < ee) {
+      ej[q] = a.e_idx[e] - slot0;
+      ew[q] = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+    }
+  }
   if (owner && part == 0) {
 #pragma unroll
     for (int k = 0; k < D; ++k) pos[k * S + lv] = x[k];
@@ -63,27 +81,59 @@ __global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
   }
   __syncthreads();
 
-  int cur = 0;
+  const T* pc = pos;
+  T* pn = pos + D * S;
   const int iters = a.forces_only ? 1 : a.iters;
   for (int it = 0; it < iters; ++it) {
-    const T* pc = pos + cur * D * S;
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
     if (owner) {
-#pragma unroll 2
-      for (int j = part; j < s; j += L) {
-        T xj[D];
+      for (int j0 = part; j0 < s; j0 += L * U) {
+        T d[U][D], r2[U], s3[U], m0[U], m1[U], m2[U];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xj[k] = pc[k * S + j];
-        pair_accumulate<T, D>(x, xj, ms[j], ms[(NM > 1 ? 1 : 0) * S + j],
-                              ms[(NM > 2 ? 2 : 0) * S + j], a.ph.eps2, f);
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * L;
+          const bool ok = j < s;
+          const int jc = ok ? j : part;  // out-of-range lanes re-read a valid column with mass 0
+          r2[u] = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[u][k] = x[k] - pc[k * S + jc];
+            r2[u] = fma(d[u][k], d[u][k], r2[u]);
+          }
+          r2[u] = Real<T>::clamp_lo(r2[u], ph.eps2);
+          m0[u] = ok ? ms[jc] : (T)0;
+          m1[u] = ok ? ms[(NM > 1 ? 1 : 0) * S + jc] : (T)0;
+          m2[u] = ok ? ms[(NM > 2 ? 2 : 0) * S + jc] : (T)0;
+        }
+        Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2, s3);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) f[k] = fma(d[u][k], s3[u], f[k]);
+        }
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] *= ci_repel;
-      for (int e = eb + part; e < ee; e += L) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (eb + part + q * L < ee) {
+          T d[D];
+          T r2 = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[k] = pc[k * S + ej[q]] - x[k];
+            r2 = fma(d[k], d[k], r2);
+          }
+          const T g = attraction_factor<T, GA>(r2, ew[q], ci, ph);
+#pragma unroll
+          for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+        }
+      }
+      for (int e = eb + part + 2 * L; e < ee; e += L) {
         const int j = a.e_idx[e] - slot0;
-        const T w = (a.e_w != nullptr && a.ph.use_weights) ? a.e_w[e] : (T)1;
+        const T w = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
         T d[D];
         T r2 = (T)0;
 #pragma unroll
@@ -91,23 +141,25 @@ __global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
           d[k] = pc[k * S + j] - x[k];
           r2 = fma(d[k], d[k], r2);
         }
-        const T g = attraction_factor<T>(r2, w, ci, a.ph);
+        const T g = attraction_factor<T, GA>(r2, w, ci, ph);
 #pragma unroll
         for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
       }
     }
+#pragma unroll
     for (int off = L >> 1; off > 0; off >>= 1) {
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
     }
-    vertex_step<T, D, ML>(x, f, fprev, E, ci, a.ph);
+    vertex_step<T, D, ML>(x, f, fprev, E, ci, ph);
     if (a.forces_only) break;
     if (owner && part == 0) {
-      T* pn = pos + (cur ^ 1) * D * S;
 #pragma unroll
       for (int k = 0; k < D; ++k) pn[k * S + lv] = x[k];
     }
-    cur ^= 1;
+    const T* tmp = pc;
+    pc = pn;
+    pn = const_cast<T*>(tmp);
     __syncthreads();
   }
 
@@ -128,7 +180,6 @@ __global__ void __launch_bounds__(1024) k_onchip_cta(const OnchipArgs<T> a) {
 
   // Epilogue: subtract the mean, divide by the largest norm (:272-303 flat / :539-564 multilevel),
   // and for the multilevel kernel map into the parent ball (:565-569).
-  const T* pc = pos + cur * D * S;
   auto block_reduce = [&](double val, bool is_max) -> double {
     for (int off = 16; off > 0; off >>= 1) {
       const double o = __shfl_xor_sync(0xffffffffu, val, off);
@@ -243,7 +294,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_onchip_warp(const OnchipA
           d[k] = pos_s[warp][cur][k][j] - x[k];
           r2 = fma(d[k], d[k], r2);
         }
-        const T gf = attraction_factor<T>(r2, w, ci, a.ph);
+        const T gf = attraction_factor<T, true>(r2, w, ci, a.ph);
 #pragma unroll
         for (int k = 0; k < D; ++k) f[k] = fma(d[k], gf, f[k]);
       }
@@ -297,13 +348,33 @@ size_t cta_smem(int dim, int max_size) {
 
 }  // namespace
 
+namespace {
+template <typename T, int D, bool ML, bool BIG, bool GA>
+const void* cta_kernel_l(int L) {
+  switch (L) {
+    case 1: return (const void*)k_onchip_cta<T, D, ML, 1, BIG, GA>;
+    case 2: return (const void*)k_onchip_cta<T, D, ML, 2, BIG, GA>;
+    case 4: return (const void*)k_onchip_cta<T, D, ML, 4, BIG, GA>;
+    case 8: return (const void*)k_onchip_cta<T, D, ML, 8, BIG, GA>;
+    case 16: return (const void*)k_onchip_cta<T, D, ML, 16, BIG, GA>;
+    default: return (const void*)k_onchip_cta<T, D, ML, 32, BIG, GA>;
+  }
+}
+template <typename T, int D, bool ML>
+const void* cta_kernel(int L, bool big, bool ga) {
+  if (big) return ga ? cta_kernel_l<T, D, ML, true, true>(L) : cta_kernel_l<T, D, ML, true, false>(L);
+  return ga ? cta_kernel_l<T, D, ML, false, true>(L) : cta_kernel_l<T, D, ML, false, false>(L);
+}
+}  // namespace
+
 template <typename T>
 void launch_onchip_cta(ge_context* ctx, const OnchipArgs<T>& a, int ntasks, int dim, bool ml,
-                       int threads, int max_size) {
+                       int lanes, int threads, int max_size) {
   if (ntasks == 0) return;
   const size_t smem = cta_smem<T>(dim, max_size);
-  const void* fn = dim == 2 ? (ml ? (const void*)k_onchip_cta<T, 2, true> : (const void*)k_onchip_cta<T, 2, false>)
-                            : (ml ? (const void*)k_onchip_cta<T, 3, true> : (const void*)k_onchip_cta<T, 3, false>);
+  const bool big = threads > 512, ga = a.ph.general_attraction != 0;
+  const void* fn = dim == 2 ? (ml ? cta_kernel<T, 2, true>(lanes, big, ga) : cta_kernel<T, 2, false>(lanes, big, ga))
+                            : (ml ? cta_kernel<T, 3, true>(lanes, big, ga) : cta_kernel<T, 3, false>(lanes, big, ga));
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&a};
@@ -323,8 +394,8 @@ void launch_onchip_warp(ge_context* ctx, const OnchipArgs<T>& a, int npacks, int
   ctx->launches++;
 }
 
-template void launch_onchip_cta<double>(ge_context*, const OnchipArgs<double>&, int, int, bool, int, int);
-template void launch_onchip_cta<float>(ge_context*, const OnchipArgs<float>&, int, int, bool, int, int);
+template void launch_onchip_cta<double>(ge_context*, const OnchipArgs<double>&, int, int, bool, int, int, int);
+template void launch_onchip_cta<float>(ge_context*, const OnchipArgs<float>&, int, int, bool, int, int, int);
 template void launch_onchip_warp<double>(ge_context*, const OnchipArgs<double>&, int, int);
 template void launch_onchip_warp<float>(ge_context*, const OnchipArgs<float>&, int, int);
 
@@ -335,9 +406,16 @@ namespace {
 
 // Lanes per vertex: the largest power of two (<= 32) such that n * L threads fit in one CTA.
 int lanes_for(int n, int max_threads) {
+  if (const char* v = std::getenv("GE_ONCHIP_LANES")) return std::atoi(v);
+  // measured on B200 (tools/profile_small.py k3sweep): 8 lanes per vertex is the sweet spot between
+  // pair-loop length and the per-warp cost of the (redundantly executed) per-vertex epilogue
   int L = 1;
-  while (L < 32 && (int64_t)n * (L * 2) <= max_threads) L *= 2;
+  while (L < 8 && (int64_t)n * (L * 2) <= max_threads) L *= 2;
   return L;
+}
+int onchip_thread_budget(int n) {
+  if (const char* v = std::getenv("GE_ONCHIP_THREADS")) return std::atoi(v);
+  return n > 64 ? 1024 : 512;
 }
 
 template <typename T>
@@ -356,21 +434,21 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
     }
     mass[i] = (T)(s + 1.0);
   }
-  DevBuf<T> d_mass(n), d_w;
-  DevBuf<int> d_I(n + 1), d_J(std::max(nnz, 1));
-  DevBuf<double> d_init((size_t)n * dim), d_out((size_t)n * dim);
-  DevBuf<int4> d_task(1);
+  DevBuf<T> d_mass(ctx, n), d_w;
+  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1));
+  DevBuf<double> d_init(ctx, (size_t)n * dim), d_out(ctx, (size_t)n * dim);
+  DevBuf<int4> d_task(ctx, 1);
   d_mass.upload(ctx, mass.data(), n);
   d_I.upload(ctx, A.indptr, n + 1);
   d_J.upload(ctx, A.indices, nnz);
   if (weighted) {
     w.resize(nnz);
     for (int e = 0; e < nnz; ++e) w[e] = (T)A.data[e];
-    d_w.alloc(std::max(nnz, 1));
+    d_w.alloc(ctx, std::max(nnz, 1));
     d_w.upload(ctx, w.data(), nnz);
   }
   d_init.upload(ctx, coords, (size_t)n * dim);
-  const int L = lanes_for(n, 1024);
+  const int L = lanes_for(n, onchip_thread_budget(n));
   const int threads = (int)round_up((int64_t)n * L, 32);
   const int4 task = make_int4(0, n, 0, L);
   d_task.upload(ctx, &task, 1);
@@ -389,7 +467,7 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   a.forces_only = forces_only ? 1 : 0;
   a.normalize = p.normalize;
   a.ph = make_physics<T>(p);
-  launch_onchip_cta<T>(ctx, a, 1, dim, false, threads, n);
+  launch_onchip_cta<T>(ctx, a, 1, dim, false, L, threads, n);
   d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
 }

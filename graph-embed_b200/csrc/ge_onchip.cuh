@@ -24,7 +24,7 @@ struct OnchipArgs {
   int64_t ld = 0;
   const double* cA_aos = nullptr;    // [m][D] parent centres
   const double* rA = nullptr;        // [m]    parent radii
-  const int4* tasks = nullptr;       // CTA tier: {slot0, size, aggregate, lanes-per-vertex}
+  const int4* tasks = nullptr;       // CTA tier: {slot0, size, aggregate, -}
                                      // warp tier: {slot0, size, aggregates in the pack, -}
   double* out_aos = nullptr;         // [n][D] final coordinates (or forces when forces_only)
   int iters = 0;
@@ -36,7 +36,7 @@ struct OnchipArgs {
 // One CTA per task (aggregate of 33..1024 members, or the whole coarsest-level graph).
 template <typename T>
 void launch_onchip_cta(ge_context* ctx, const OnchipArgs<T>& a, int ntasks, int dim, bool ml,
-                       int threads, int max_size);
+                       int lanes, int threads, int max_size);
 // One warp per pack of equal-size aggregates (2..32 members, also singletons in forces mode).
 template <typename T>
 void launch_onchip_warp(ge_context* ctx, const OnchipArgs<T>& a, int npacks, int dim);

@@ -103,6 +103,12 @@ ge_status ge_context_create(int device, void* cuda_stream, ge_context** out);
 void ge_context_destroy(ge_context* ctx);
 /* Kernels launched by this context since creation (the library counts its own launches). */
 int64_t ge_context_launch_count(const ge_context* ctx);
+/* Bytes this context copied host->device / device->host since creation. */
+void ge_context_bytes(const ge_context* ctx, double* h2d, double* d2h);
+/* Roofline denominator for the repulsion kernels: sustained FMA rate (TFLOP/s, 2 flops per FMA)
+ * of the FP64 or FP32 pipe, measured with a register-resident independent-FMA kernel over all
+ * SMs and timed with CUDA events. */
+ge_status ge_measure_fma_peak(ge_context* ctx, int precision, double* tflops);
 
 /* ---- the reference's kernels, host buffers in and out ------------------------------------ */
 
@@ -178,6 +184,10 @@ void ge_flat_plan_swap(ge_flat_plan* plan);
 /* Convenience: `iters` x (launch_iteration + swap), single rank. */
 ge_status ge_flat_plan_iterate(ge_flat_plan* plan, int iters);
 ge_status ge_flat_plan_sync(ge_flat_plan* plan);
+/* Measurement hook: which kernels launch_iteration runs (bit 0 = repulsion, bit 1 = attraction +
+ * step; default 3).  Lets the HBM-bound attraction kernel be timed alone on graphs whose
+ * all-pairs repulsion would take seconds. */
+void ge_flat_plan_select_kernels(ge_flat_plan* plan, int mask);
 /* Per-kernel device time.  enable != 0 brackets each launch with CUDA events on the launching
  * stream; get returns the accumulated milliseconds and launch counts since the last reset. */
 void ge_flat_plan_profile(ge_flat_plan* plan, int enable);

@@ -15,7 +15,7 @@ def _graph(graphs, name):
     if name == "rgg2000":
         return graphs.rgg(2000, 10.0, seed=1)
     if name == "galerkin":  # weighted, with self-loops (quirk Q5)
-        A = graphs.rgg(3000, 10.0, seed=2)
+        A = graphs.rgg(2400, 10.0, seed=2)
         As, _ = graphs.coarsen(A, 0.25, min_coarse=200, max_levels=1)
         return As[1]
     raise KeyError(name)
