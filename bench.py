@@ -161,7 +161,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     entry.load_package()
-    from graph_embed_b200 import capi, graphs
+    from graph_embed_b200 import capi, graphs, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,9 +188,7 @@ def run_ours(args):
     x0 = capi.reference_uniform(23, n * dim).reshape(n, dim)
 
     # row blocks: ld is a multiple of 256, hence of every N in {1,2,4,8}
-    probe_ld = ((n + 255) // 256) * 256
-    R = probe_ld // world
-    r0, r1 = min(n, rank * R), min(n, (rank + 1) * R)
+    r0, r1, R, probe_ld = sharding.row_block(n, world, rank)
     plan = ctx.flat_plan(A, dim, params, rows=(r0, r1))
     ld = plan.ld
     assert ld == probe_ld
@@ -203,10 +201,8 @@ def run_ours(args):
 
     def one_step():
         plan.launch_iteration()
-        if world > 1:
-            nxt = ptr_to_buf[plan.next_ptr()].view(dim, ld)
-            for k in range(dim):  # in-place: own slice sits at rank*R of the output
-                dist.all_gather_into_tensor(nxt[k], nxt[k, rank * R:(rank + 1) * R])
+        if world > 1:  # in-place: own slice sits at rank*R of the output
+            sharding.allgather_coords(dist, ptr_to_buf[plan.next_ptr()].view(dim, ld), rank, R)
         plan.swap()
 
     def barrier():
@@ -281,7 +277,7 @@ def run_ours(args):
                "roofline": roof, "roofline_attraction": roof2}
 
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------
-    e2e = bench_e2e(args, torch, dist, capi, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier)
+    e2e = bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier)
     if rank == 0:
         out["e2e"] = e2e
 
@@ -301,7 +297,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_e2e(args, torch, dist, capi, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier):
+def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier):
     """Same metric through the public host-buffer API, host<->device copies inside the timed
     region.  N = 1: ge_flat_forceatlas (the forceAtlas drop-in: graph + coordinates in from pinned
     host memory, coordinates out), one call per step.  N > 1: the row-block plan API with the
@@ -331,9 +327,7 @@ def bench_e2e(args, torch, dist, capi, ctx, plan, A, x0, world, rank, R, ptr_to_
         for _ in range(steps):
             plan.upload(x)
             plan.launch_iteration()
-            nxt = ptr_to_buf[plan.next_ptr()].view(dim, ld)
-            for k in range(dim):
-                dist.all_gather_into_tensor(nxt[k], nxt[k, rank * R:(rank + 1) * R])
+            sharding.allgather_coords(dist, ptr_to_buf[plan.next_ptr()].view(dim, ld), rank, R)
             plan.swap()
             x = plan.download()
         barrier()

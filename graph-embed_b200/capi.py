@@ -41,7 +41,8 @@ class Params(C.Structure):
 
 class EmbedOptions(C.Structure):
     _fields_ = [("coarse_iterations", C.c_int32), ("level_iterations", C.c_int32),
-                ("precision", C.c_int32), ("seed", C.c_uint32), ("verbose", C.c_int32)]
+                ("precision", C.c_int32), ("seed", C.c_uint32), ("verbose", C.c_int32),
+                ("first_layer", C.c_int32)]
 
 
 class EmbedStats(C.Structure):
@@ -224,7 +225,7 @@ class Context:
         return out
 
     def embed(self, As, P_Ts, dim, seed=0, precision=GE_F64, coarse_iterations=100000,
-              level_iterations=100, verbose=False):
+              level_iterations=100, verbose=False, return_level1=False):
         L = len(P_Ts)
         assert len(As) == L + 1
         av = [CsrView(A) for A in As]
@@ -236,9 +237,13 @@ class Context:
         opt.seed, opt.precision, opt.verbose = int(seed), int(precision), int(verbose)
         opt.coarse_iterations, opt.level_iterations = int(coarse_iterations), int(level_iterations)
         out = np.zeros((As[0].shape[0], dim))
+        m = As[1].shape[0] if L else 0
+        r_A, coords_A = np.zeros(max(m, 1)), np.zeros((max(m, 1), dim))
         stats = EmbedStats()
         _check(lib().ge_embed(self.h, L, a_arr, p_arr, int(dim), C.byref(opt), _ptr(out, _pd),
-                              C.byref(stats)))
+                              _ptr(r_A, _pd), _ptr(coords_A, _pd), C.byref(stats)))
+        if return_level1:
+            return out, stats.as_dict(), r_A[:m], coords_A[:m]
         return out, stats.as_dict()
 
     # -- parity hooks -------------------------------------------------------------------------

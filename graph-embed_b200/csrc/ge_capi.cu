@@ -280,7 +280,7 @@ struct EmbedRun {
     const ge_csr& A = As[l];
     const int n = A.rows;
     if (l == L) {  // :582-587
-      if (opt.verbose) std::printf("embedding layer %d: getting base coords\n", l + 1);
+      if (opt.verbose) std::printf("embedding layer %d: getting base coords\n", l + opt.first_layer);
       r_A.clear();
       coords_A.clear();
       std::vector<double> coords((size_t)n * dim);
@@ -300,7 +300,7 @@ struct EmbedRun {
     coords_A = level(l + 1, r_Ac, coords_Ac);  // :593
     const ge_csr& P = Ps[l];
     const int m = P.rows;
-    if (opt.verbose) std::printf("embeding layer %d\n", l + 1);
+    if (opt.verbose) std::printf("embeding layer %d\n", l + opt.first_layer);
     const double t0 = now_ms();
     r_A.assign(m, 0.0);
     if (r_Ac.empty())
@@ -395,6 +395,7 @@ void ge_embed_options_default(ge_embed_options* o) {
   o->level_iterations = 100;
   o->precision = GE_F64;
   o->verbose = 1;
+  o->first_layer = 1;
 }
 
 ge_status ge_context_create(int device, void* cuda_stream, ge_context** out) {
@@ -490,7 +491,8 @@ ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_cs
 }
 
 ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr* P_Ts, int dim,
-                   const ge_embed_options* opt, double* coords_out, ge_embed_stats* stats) {
+                   const ge_embed_options* opt, double* coords_out, double* r_A_out,
+                   double* coords_A_out, ge_embed_stats* stats) {
   return guarded([&] {
     require_ctx(ctx);
     GE_REQUIRE(n_levels >= 0 && As != nullptr && coords_out != nullptr, "null argument");
@@ -515,6 +517,9 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     std::vector<double> r_A, coords_A;
     std::vector<double> coords = run.level(0, r_A, coords_A);
     std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
+    if (r_A_out && !r_A.empty()) std::memcpy(r_A_out, r_A.data(), r_A.size() * sizeof(double));
+    if (coords_A_out && !coords_A.empty())
+      std::memcpy(coords_A_out, coords_A.data(), coords_A.size() * sizeof(double));
     run.st.total_ms = now_ms() - t0;
     run.st.kernel_launches = ctx->launches - launches0;
     run.st.h2d_bytes = ctx->h2d_bytes - h0;

@@ -1,0 +1,73 @@
+// graph-embed_b200 drop-in :: glue between the reference's C++ types and the C ABI.
+#ifndef GE_B200_RUNTIME_HPP
+#define GE_B200_RUNTIME_HPP
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "graph_embed_b200.h"
+#include "matrixutils.hpp"
+
+namespace ge_b200 {
+
+// Process-wide context on the current CUDA device (the reference keeps no state either; the
+// context only owns a stream and the device memory pool).
+inline ge_context* default_context() {
+  struct Holder {
+    ge_context* ctx = nullptr;
+    Holder() {
+      if (ge_context_create(-1, nullptr, &ctx) != GE_OK)
+        throw std::runtime_error(std::string("graph-embed_b200: ") + ge_last_error());
+    }
+    ~Holder() { ge_context_destroy(ctx); }
+  };
+  static Holder h;
+  return h.ctx;
+}
+
+// The reference reports problems through assert() only (src/embed.cpp:564-570); the drop-in
+// throws instead of continuing with garbage, because there is no CPU path to fall back to.
+inline void check(ge_status st) {
+  if (st != GE_OK) throw std::runtime_error(std::string("graph-embed_b200: ") + ge_last_error());
+}
+
+inline ge_csr view(const SparseMatrix& A) {
+  ge_csr c;
+  c.rows = A.Rows();
+  c.cols = A.Cols();
+  c.nnz = static_cast<int64_t>(A.GetIndices().size());
+  c.indptr = A.GetIndptr().data();
+  c.indices = A.GetIndices().data();
+  c.data = A.GetData().data();
+  return c;
+}
+
+inline std::vector<double> flatten(const std::vector<std::vector<double>>& c, int d) {
+  std::vector<double> x(c.size() * static_cast<size_t>(d));
+  for (size_t i = 0; i < c.size(); ++i)
+    for (int k = 0; k < d; ++k) x[i * d + k] = c[i][k];
+  return x;
+}
+
+inline std::vector<std::vector<double>> unflatten(const std::vector<double>& x, int n, int d) {
+  std::vector<std::vector<double>> c(n, std::vector<double>(d));
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < d; ++k) c[i][k] = x[static_cast<size_t>(i) * d + k];
+  return c;
+}
+
+// Knobs the reference does not have (precision, seed); change before calling partition::embed.
+struct Options {
+  int precision = GE_F64;
+  unsigned seed = 0;   // 0: std::random_device like the reference
+  bool verbose = true; // print the reference's "embedding layer N" progress lines
+};
+inline Options& options() {
+  static Options o;
+  return o;
+}
+
+}  // namespace ge_b200
+
+#endif

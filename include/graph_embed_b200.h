@@ -72,6 +72,7 @@ typedef struct ge_embed_options {
   int32_t precision;         /* ge_precision */
   uint32_t seed;             /* 0 = std::random_device; else every stream = std::mt19937(seed) */
   int32_t verbose;           /* 1 = print the reference's "embedding layer N" lines (src/embed.cpp:583,613) */
+  int32_t first_layer;       /* layer number printed for As[0] (1; embedMultilevel from level k passes k+1) */
 } ge_embed_options;
 
 /* Per-call statistics filled by ge_embed (all optional to read). */
@@ -132,9 +133,12 @@ ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_cs
 /* partition::embed(As, P_Ts, d)  src/embed.cpp:561-574, i.e. the embedMultilevel recursion of
  * :576-796: coarsest level flat solve, then per level radii + rescale (:615-777, host) and the
  * per-aggregate solve + prolongation.  As: n_levels + 1 matrices, P_Ts: n_levels.
- * coords_out: As[0].rows x dim.  opt / stats may be NULL. */
+ * coords_out: As[0].rows x dim.  r_A_out (As[1].rows) / coords_A_out (As[1].rows x dim), when not
+ * NULL and n_levels > 0, receive what embedMultilevel leaves in its r_A / coords_A out-parameters:
+ * the radii and rescaled coordinates of level 1.  opt / stats may be NULL. */
 ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr* P_Ts, int dim,
-                   const ge_embed_options* opt, double* coords_out, ge_embed_stats* stats);
+                   const ge_embed_options* opt, double* coords_out, double* r_A_out,
+                   double* coords_A_out, ge_embed_stats* stats);
 
 /* ---- parity hooks: forces of ONE iteration from given positions --------------------------- */
 /* include/forceatlas.hpp:148-212 -> forces (n x dim).  `path`: 0 = auto, 1 = tiled multi-CTA

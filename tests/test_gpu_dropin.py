@@ -1,0 +1,36 @@
+"""The C++ drop-in (graph-embed_b200/host/include/embed.hpp) compiled against the reference's own
+interface and run on the GPU, and the embedMultilevel out-parameters of ge_embed."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import load_hier_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_dropin_demo_runs(capi):
+    exe = os.path.join(ROOT, "graph-embed_b200", "lib", "ge_dropin_demo")
+    if not os.path.exists(exe):
+        from graph_embed_b200 import build
+        build.build_all()
+    for args in (["48", "2"], ["32", "3"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "embedded! in time" in r.stdout and "embedVia ok" in r.stdout
+        assert "getting base coords" in r.stdout  # the reference's progress lines (src/embed.cpp:583)
+
+
+def test_embed_level1_outputs_match_oracle(ctx, capi, oracle):
+    """r_A / coords_A out-parameters of embedMultilevel (src/embed.cpp:580-581): recomputed here by
+    running the oracle's radii step on the coordinates of a short embed of the coarser levels."""
+    As, Ps, _ = load_hier_golden()
+    x, _, r_A, coords_A = ctx.embed(As, Ps, 2, seed=9, coarse_iterations=20, level_iterations=3,
+                                    return_level1=True)
+    sub, _, r_Ac, coords_Ac = ctx.embed(As[1:], Ps[1:], 2, seed=9, coarse_iterations=20,
+                                        level_iterations=3, return_level1=True)
+    cA, rA = oracle.radii(sub, 2, As[1], Ps[1], coords_Ac, r_Ac)
+    assert np.abs(coords_A - cA).max() < 1e-9 and np.abs(r_A - rA).max() < 1e-9
