@@ -84,7 +84,7 @@ struct VecLoad<float, 4> {
 // tail of one row block, sweeps whole row blocks, and starts the head of another.  Whole blocks
 // are written straight to F; shared blocks go to the CTA's two partial slots and are summed in a
 // fixed order by k_repulsion_fixup (deterministic, no atomics).
-template <typename T, int D, int IPT>
+template <typename T, int D, int IPT, int JU>
 __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a) {
   constexpr int NM = Real<T>::kMassArrays;
   constexpr int NA = D + NM;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
       mbar_wait(&full[s], (gl / kRepStages) & 1u);
       const T* st = tiles + (size_t)s * NA * kTileJ;
 
-#pragma unroll 1
+#pragma unroll JU
       for (int jj = 0; jj < kTileJ; jj += VEC) {
         T xj[D][VEC], mj[3][VEC];
 #pragma unroll
@@ -415,28 +415,32 @@ size_t repulsion_smem(int dim) {
          kRepStages * sizeof(uint64_t);
 }
 
+template <typename T, int D, int JU>
+const void* repulsion_kernel_d(int ipt) {
+  return ipt == 1 ? (const void*)k_repulsion<T, D, 1, JU>
+                  : ipt == 2 ? (const void*)k_repulsion<T, D, 2, JU> : (const void*)k_repulsion<T, D, 4, JU>;
+}
 template <typename T>
-const void* repulsion_kernel(int dim, int ipt) {
-  if (dim == 2)
-    return ipt == 1 ? (const void*)k_repulsion<T, 2, 1>
-                    : ipt == 2 ? (const void*)k_repulsion<T, 2, 2> : (const void*)k_repulsion<T, 2, 4>;
-  return ipt == 1 ? (const void*)k_repulsion<T, 3, 1>
-                  : ipt == 2 ? (const void*)k_repulsion<T, 3, 2> : (const void*)k_repulsion<T, 3, 4>;
+const void* repulsion_kernel(int dim, int ipt, int ju) {
+  if (dim == 2) return ju == 1 ? repulsion_kernel_d<T, 2, 1>(ipt) : repulsion_kernel_d<T, 2, 2>(ipt);
+  return ju == 1 ? repulsion_kernel_d<T, 3, 1>(ipt) : repulsion_kernel_d<T, 3, 2>(ipt);
 }
 }  // namespace
 
 template <typename T>
 RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowSegment>& segments)
     : ctx_(ctx), dim_(dim) {
-  // Launch shape measured on B200 (tools/sweep_rep.py): 512 threads, 2 rows per thread in FP64
-  // (56-64 registers -> 2 CTAs = 32 warps per SM), 4 rows per thread in FP32.  Small sweeps use
-  // narrower CTAs so that there are enough (row block, tile) units to share out.
+  // Launch shape measured on B200 (tools/sweep_rep.py; every shape lands within 10 % because the
+  // kernel is issue-bound): 512 threads, 2 rows per thread (4 for FP64 d = 3), the
+  // column loop unrolled twice.  Small sweeps use narrower CTAs so that there are enough
+  // (row block, tile) units to share out.
   long long total_rows = 0;
   for (const auto& sg : segments) total_rows += sg.row1 - sg.row0;
-  ipt_ = env_int("GE_REP_IPT", sizeof(T) == 8 ? 2 : 4);
+  ipt_ = env_int("GE_REP_IPT", (sizeof(T) == 8 && dim == 3) ? 4 : 2);
   threads_ = env_int("GE_REP_THREADS", 512);
   while (threads_ > 128 && total_rows < (long long)ctx->sm_count * threads_ * ipt_) threads_ /= 2;
-  const void* fn = repulsion_kernel<T>(dim_, ipt_);
+  ju_ = env_int("GE_REP_JU", 2);
+  const void* fn = repulsion_kernel<T>(dim_, ipt_, ju_);
   const size_t smem = repulsion_smem<T>(dim_);
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,7 +488,7 @@ void RepulsionPlan<T>::launch(const T* pos, const T* mass, int64_t ld, T* F, int
   a.repel = repel;
   a.eps2 = eps2;
   void* args[] = {(void*)&a};
-  GE_CUDA(cudaLaunchKernel(repulsion_kernel<T>(dim_, ipt_), dim3(grid_), dim3(threads_), args,
+  GE_CUDA(cudaLaunchKernel(repulsion_kernel<T>(dim_, ipt_, ju_), dim3(grid_), dim3(threads_), args,
                            repulsion_smem<T>(dim_), ctx_->stream));
   ctx_->launches++;
   if (dim_ == 2) k_repulsion_fixup<T, 2><<<nblocks_, 256, 0, ctx_->stream>>>(a, grid_);

@@ -55,7 +55,7 @@ class RepulsionPlan {
 
  private:
   ge_context* ctx_;
-  int dim_, threads_ = 512, ipt_ = 2, grid_ = 0, nblocks_ = 0;
+  int dim_, threads_ = 512, ipt_ = 2, ju_ = 1, grid_ = 0, nblocks_ = 0;
   long long total_units_ = 0;
   DevBuf<BlockDesc> blocks_;
   DevBuf<T> partial_;

@@ -21,9 +21,10 @@ x0 = capi.reference_uniform(23, n * dim).reshape(n, dim)
 ctx = capi.Context(0)
 print("peak TF", ctx.fma_peak_tflops(prec))
 flops = float(n) * (n - 1) * (5 * dim + 4)
-for ipt in (1, 2, 4):
-    for thr in (128, 192, 256, 320, 384, 448, 512):
-        os.environ["GE_REP_THREADS"], os.environ["GE_REP_IPT"] = str(thr), str(ipt)
+import itertools
+for ju, ipt, thr in itertools.product((1, 2), (1, 2, 4), (128, 256, 512)):
+    if True:
+        os.environ["GE_REP_THREADS"], os.environ["GE_REP_IPT"], os.environ["GE_REP_JU"] = str(thr), str(ipt), str(ju)
         try:
             plan = ctx.flat_plan(A, dim, capi.flat_params(precision=prec))
         except capi.GeError as e:
@@ -36,5 +37,5 @@ for ipt in (1, 2, 4):
         plan.iterate(2)
         p = plan.profile_get()
         ms = p["repulsion_ms"] / p["repulsion_launches"]
-        print("ipt=%d thr=%3d  %.2f ms  %.2f TF" % (ipt, thr, ms, flops / ms / 1e9), flush=True)
+        print("ju=%d ipt=%d thr=%3d  %.2f ms  %.2f TF" % (ju, ipt, thr, ms, flops / ms / 1e9), flush=True)
         plan.close()
