@@ -60,7 +60,7 @@ SYMBOLS = [
     "ge_version", "ge_last_error", "ge_params_default_flat", "ge_params_default_multilevel",
     "ge_embed_options_default", "ge_context_create", "ge_context_destroy",
     "ge_context_launch_count", "ge_context_bytes", "ge_measure_fma_peak",
-    "ge_flat_forceatlas", "ge_multilevel_forceatlas", "ge_embed",
+    "ge_flat_forceatlas", "ge_multilevel_forceatlas", "ge_multilevel_forceatlas_shard", "ge_embed",
     "ge_flat_forces", "ge_multilevel_forces", "ge_level_radii", "ge_reference_uniform",
     "ge_flat_plan_create", "ge_flat_plan_destroy", "ge_flat_plan_ld", "ge_flat_plan_elem_size",
     "ge_flat_plan_bind_coords", "ge_flat_plan_upload_coords", "ge_flat_plan_download_coords",
@@ -212,16 +212,22 @@ class Context:
         _check(lib().ge_flat_forceatlas(self.h, a.ref(), int(dim), _ptr(x, _pd), C.byref(params)))
         return x
 
-    def multilevel_forceatlas(self, A, P_T, coords_A, r_A, dim, params, init=None):
+    def multilevel_forceatlas(self, A, P_T, coords_A, r_A, dim, params, init=None, aggregates=None):
+        """aggregates=(begin, end): solve only that range (rows of other aggregates come back 0)."""
         a, p = CsrView(A), CsrView(P_T, with_data=False)
         n, m = A.shape[0], P_T.shape[0]
         v_A = vertex_to_aggregate(P_T)
         cA, rA = _f64(coords_A).reshape(m, dim), _f64(r_A)
         x0 = None if init is None else _f64(init).reshape(n, dim)
         out = np.zeros((n, dim))
-        _check(lib().ge_multilevel_forceatlas(self.h, a.ref(), p.ref(), _ptr(v_A, _pi),
-                                              _ptr(cA, _pd), _ptr(rA, _pd), _ptr(x0, _pd),
-                                              _ptr(out, _pd), int(dim), C.byref(params)))
+        if aggregates is None:
+            _check(lib().ge_multilevel_forceatlas(self.h, a.ref(), p.ref(), _ptr(v_A, _pi),
+                                                  _ptr(cA, _pd), _ptr(rA, _pd), _ptr(x0, _pd),
+                                                  _ptr(out, _pd), int(dim), C.byref(params)))
+        else:
+            _check(lib().ge_multilevel_forceatlas_shard(
+                self.h, a.ref(), p.ref(), _ptr(v_A, _pi), _ptr(cA, _pd), _ptr(rA, _pd), _ptr(x0, _pd),
+                _ptr(out, _pd), int(dim), C.byref(params), int(aggregates[0]), int(aggregates[1])))
         return out
 
     def embed(self, As, P_Ts, dim, seed=0, precision=GE_F64, coarse_iterations=100000,

@@ -490,6 +490,32 @@ ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_cs
   });
 }
 
+ge_status ge_multilevel_forceatlas_shard(ge_context* ctx, const ge_csr* A, const ge_csr* P_T,
+                                         const int32_t* v_A, const double* coords_A,
+                                         const double* r_A, const double* init, double* coords,
+                                         int dim, const ge_params* p, int32_t agg_begin,
+                                         int32_t agg_end) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(v_A && coords_A && r_A && coords && p, "null argument");
+    std::vector<double> drawn;
+    if (init == nullptr) {  // every rank draws the whole level's stream: identical on all ranks
+      GE_REQUIRE(p->seed != 0, "sharded solve with init == NULL needs a fixed seed shared by all ranks");
+      drawn.resize((size_t)A->rows * dim);
+      std::mt19937 gen(p->seed);
+      std::uniform_real_distribution<double> random(-1.0, 1.0);
+      for (int a = 0; a < P_T->rows; ++a)
+        for (int c = P_T->indptr[a]; c < P_T->indptr[a + 1]; ++c)
+          for (int k = 0; k < dim; ++k) drawn[(size_t)P_T->indices[c] * dim + k] = random(gen);
+      init = drawn.data();
+    }
+    multilevel_solve(ctx, *A, *P_T, v_A, coords_A, r_A, init, coords, dim, *p, false, nullptr,
+                     agg_begin, agg_end);
+  });
+}
+
 ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr* P_Ts, int dim,
                    const ge_embed_options* opt, double* coords_out, double* r_A_out,
                    double* coords_A_out, ge_embed_stats* stats) {

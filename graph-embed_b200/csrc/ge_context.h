@@ -120,7 +120,7 @@ void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_param
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
-                      double* pairs_out);
+                      double* pairs_out, int agg_begin = 0, int agg_end = -1);
 
 // ---- ge_host.cpp -----------------------------------------------------------------------------
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,

@@ -229,7 +229,7 @@ template <typename T>
 void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
                   const double* coords_A, const double* r_A, const double* init,
                   double* coords_out, int dim, const ge_params& p, bool forces_only,
-                  double* pairs_out) {
+                  double* pairs_out, int agg_begin, int agg_end) {
   constexpr int NM = Real<T>::kMassArrays;
   const int n = A.rows, m = P.rows;
   const int nnz = A.indptr[n];
@@ -240,7 +240,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   std::vector<int> by_size[33];
   std::vector<int> cta_aggs, grid_aggs;
   double pairs = 0.0;
-  for (int a = 0; a < m; ++a) {
+  for (int a = agg_begin; a < agg_end; ++a) {
     const int s = P.indptr[a + 1] - P.indptr[a];
     pairs += double(s) * double(s - 1);
     if (s <= 0) continue;
@@ -304,7 +304,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   const int nslots = (int)cursor;
   const int64_t ld = round_up(std::max(nslots, 1), kTileJ);
   std::vector<int> vtx((size_t)ld, -1), slot_of(std::max(n, 1), -1), agg_of_slot((size_t)ld, -1);
-  for (int a = 0; a < m; ++a) {
+  for (int a = agg_begin; a < agg_end; ++a) {
     const int s = size_of(a);
     for (int i = 0; i < s; ++i) {
       const int v = P.indices[P.indptr[a] + i];
@@ -335,6 +335,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   d_init.upload(ctx, init, (size_t)n * dim);
   d_eb.zero(ctx->stream);
   d_ee.zero(ctx->stream);
+  if (agg_begin > 0 || agg_end < m) d_out.zero(ctx->stream);  // rows of other ranks' aggregates
 
   // ---- prep --------------------------------------------------------------------------------
   PrepArgs<T> pa;
@@ -483,15 +484,17 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
-                      double* pairs_out) {
+                      double* pairs_out, int agg_begin, int agg_end) {
+  if (agg_end < 0) agg_end = P_T.rows;
+  GE_REQUIRE(0 <= agg_begin && agg_begin <= agg_end && agg_end <= P_T.rows, "bad aggregate range");
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
   GE_REQUIRE(A.rows == A.cols, "A must be square");
   GE_REQUIRE(P_T.cols == A.rows, "P_T.cols must equal A.rows");
   GE_REQUIRE(P_T.indptr[P_T.rows] == A.rows, "P_T must list every vertex exactly once");
   if (p.precision == GE_F32)
-    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out);
+    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end);
   else
-    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out);
+    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end);
 }
 
 }  // namespace ge

@@ -17,11 +17,75 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "ge_onchip.cuh"
 
 namespace ge {
 
 namespace {
+
+// Shared-memory column records: positions are AoS with DP = 2 (d = 2) or 4 (d = 3, one pad) reals
+// per column, masses AoS (c, 1.5c, 1.875c, pad) in FP64 / (c) in FP32, so that one column is
+// fetched with 16-byte shared loads; both arrays are padded with zero-mass columns up to a
+// multiple of the pair-loop trip width, which removes every bounds predicate from the loop.
+template <typename T, int D>
+struct Col;
+template <>
+struct Col<double, 2> {
+  static constexpr int DP = 2, MP = 4;
+  __device__ __forceinline__ static void pos(const double* b, int j, double (&x)[2]) {
+    const double2 v = reinterpret_cast<const double2*>(b)[j];
+    x[0] = v.x;
+    x[1] = v.y;
+  }
+  __device__ __forceinline__ static void mass(const double* b, int j, double& m0, double& m1, double& m2) {
+    const double2 v = reinterpret_cast<const double2*>(b)[2 * j];
+    m0 = v.x;
+    m1 = v.y;
+    m2 = b[4 * j + 2];
+  }
+};
+template <>
+struct Col<double, 3> {
+  static constexpr int DP = 4, MP = 4;
+  __device__ __forceinline__ static void pos(const double* b, int j, double (&x)[3]) {
+    const double2 v = reinterpret_cast<const double2*>(b)[2 * j];
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = b[4 * j + 2];
+  }
+  __device__ __forceinline__ static void mass(const double* b, int j, double& m0, double& m1, double& m2) {
+    Col<double, 2>::mass(b, j, m0, m1, m2);
+  }
+};
+template <>
+struct Col<float, 2> {
+  static constexpr int DP = 2, MP = 1;
+  __device__ __forceinline__ static void pos(const float* b, int j, float (&x)[2]) {
+    const float2 v = reinterpret_cast<const float2*>(b)[j];
+    x[0] = v.x;
+    x[1] = v.y;
+  }
+  __device__ __forceinline__ static void mass(const float* b, int j, float& m0, float& m1, float& m2) {
+    m0 = m1 = m2 = b[j];
+  }
+};
+template <>
+struct Col<float, 3> {
+  static constexpr int DP = 4, MP = 1;
+  __device__ __forceinline__ static void pos(const float* b, int j, float (&x)[3]) {
+    const float4 v = reinterpret_cast<const float4*>(b)[j];
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = v.z;
+  }
+  __device__ __forceinline__ static void mass(const float* b, int j, float& m0, float& m1, float& m2) {
+    m0 = m1 = m2 = b[j];
+  }
+};
+
+__host__ __device__ inline int onchip_spad(int s, int L, int U) { return (s + L * U - 1) / (L * U) * (L * U); }
 
 // BIG = false: up to 512 threads (128 registers each), U = 4 independent pairs per trip of the pair
 // loop (instruction-level parallelism); BIG = true: up to 1024 threads (64 registers), U = 2 and
@@ -37,9 +101,11 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
 
   const int4 task = a.tasks[blockIdx.x];
   const int slot0 = task.x, s = task.y, agg = task.z;
-  const int S = (s + 1) & ~1;
-  T* pos = reinterpret_cast<T*>(smem_raw);  // [2][D][S]
-  T* ms = pos + 2 * D * S;                  // [NM][S]
+  using C = Col<T, D>;
+  constexpr int DP = C::DP, MP = C::MP;
+  const int S = onchip_spad(s, L, U);
+  T* pos = reinterpret_cast<T*>(smem_raw);  // [2][S][DP]
+  T* ms = pos + 2 * S * DP;                 // [S][MP]
 
   const int tid = threadIdx.x;
   const int lv = tid / L;
@@ -72,40 +138,40 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
       ew[q] = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
     }
   }
+  for (int i = tid; i < 2 * S * DP + S * MP; i += blockDim.x) pos[i] = (T)0;  // zero-mass padding
+  __syncthreads();
   if (owner && part == 0) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) pos[k * S + lv] = x[k];
-    ms[lv] = ci;
-    if (NM > 1) ms[S + lv] = (T)1.5 * ci;
-    if (NM > 2) ms[2 * S + lv] = (T)1.875 * ci;
+    for (int k = 0; k < D; ++k) pos[lv * DP + k] = x[k];
+    ms[lv * MP] = ci;
+    if (NM > 1) ms[lv * MP + (NM > 1 ? 1 : 0)] = (T)1.5 * ci;
+    if (NM > 2) ms[lv * MP + (NM > 2 ? 2 : 0)] = (T)1.875 * ci;
   }
   __syncthreads();
 
   const T* pc = pos;
-  T* pn = pos + D * S;
+  T* pn = pos + S * DP;
   const int iters = a.forces_only ? 1 : a.iters;
   for (int it = 0; it < iters; ++it) {
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
     if (owner) {
-      for (int j0 = part; j0 < s; j0 += L * U) {
+      for (int j0 = part; j0 < S; j0 += L * U) {
         T d[U][D], r2[U], s3[U], m0[U], m1[U], m2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * L;
-          const bool ok = j < s;
-          const int jc = ok ? j : part;  // out-of-range lanes re-read a valid column with mass 0
+          T xj[D];
+          C::pos(pc, j, xj);
+          C::mass(ms, j, m0[u], m1[u], m2[u]);
           r2[u] = (T)0;
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            d[u][k] = x[k] - pc[k * S + jc];
+            d[u][k] = x[k] - xj[k];
             r2[u] = fma(d[u][k], d[u][k], r2[u]);
           }
           r2[u] = Real<T>::clamp_lo(r2[u], ph.eps2);
-          m0[u] = ok ? ms[jc] : (T)0;
-          m1[u] = ok ? ms[(NM > 1 ? 1 : 0) * S + jc] : (T)0;
-          m2[u] = ok ? ms[(NM > 2 ? 2 : 0) * S + jc] : (T)0;
         }
         Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2, s3);
 #pragma unroll
@@ -119,11 +185,12 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (eb + part + q * L < ee) {
-          T d[D];
+          T xj[D], d[D];
+          C::pos(pc, ej[q], xj);
           T r2 = (T)0;
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            d[k] = pc[k * S + ej[q]] - x[k];
+            d[k] = xj[k] - x[k];
             r2 = fma(d[k], d[k], r2);
           }
           const T g = attraction_factor<T, GA>(r2, ew[q], ci, ph);
@@ -134,11 +201,12 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
       for (int e = eb + part + 2 * L; e < ee; e += L) {
         const int j = a.e_idx[e] - slot0;
         const T w = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
-        T d[D];
+        T xj[D], d[D];
+        C::pos(pc, j, xj);
         T r2 = (T)0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          d[k] = pc[k * S + j] - x[k];
+          d[k] = xj[k] - x[k];
           r2 = fma(d[k], d[k], r2);
         }
         const T g = attraction_factor<T, GA>(r2, w, ci, ph);
@@ -155,7 +223,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
     if (a.forces_only) break;
     if (owner && part == 0) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) pn[k * S + lv] = x[k];
+      for (int k = 0; k < D; ++k) pn[lv * DP + k] = x[k];
     }
     const T* tmp = pc;
     pc = pn;
@@ -203,7 +271,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     double part_sum = 0.0;
-    for (int i = tid; i < s; i += blockDim.x) part_sum += (double)pc[k * S + i];
+    for (int i = tid; i < s; i += blockDim.x) part_sum += (double)pc[i * DP + k];
     const double tot = block_reduce(part_sum, false);
     if (tid == 0) bc[k] = tot / s;
   }
@@ -213,7 +281,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
     double m2 = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const double c = (double)pc[k * S + i] - bc[k];
+      const double c = (double)pc[i * DP + k] - bc[k];
       m2 += c * c;
     }
     mx = fmax(mx, sqrt(m2));
@@ -224,10 +292,214 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
     const int vi = a.vtx ? a.vtx[slot0 + i] : slot0 + i;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const double c = ((double)pc[k * S + i] - bc[k]) / maxlen;
+      const double c = ((double)pc[i * DP + k] - bc[k]) / maxlen;
       a.out_aos[(int64_t)vi * D + k] =
           ML ? a.cA_aos[(int64_t)agg * D + k] + a.rA[agg] * c : c;
     }
+  }
+}
+
+// K3 across a thread-block cluster: the coarsest-level flat solve with the vertices split over the
+// C CTAs of one cluster (C SMs instead of one).  Every CTA keeps the full, double-buffered position
+// array in its own shared memory; after the per-vertex epilogue the owning lanes store the new
+// position into the NEXT buffer of every CTA of the cluster through distributed shared memory, and
+// one cluster barrier per iteration (arrive.release / wait.acquire) publishes them.  Still zero
+// launches and zero global-memory traffic per iteration.
+template <typename T, int D, int L, bool GA>
+__global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, int per_cta) {
+  namespace cg = cooperative_groups;
+  constexpr int NM = Real<T>::kMassArrays;
+  constexpr int U = 4;
+  using C = Col<T, D>;
+  constexpr int DP = C::DP, MP = C::MP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  __shared__ double bc[D + 1];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+
+  const int4 task = a.tasks[0];
+  const int s = task.y;
+  const int S = onchip_spad(s, L, U);
+  T* pos = reinterpret_cast<T*>(smem_raw);  // [2][S][DP]
+  T* ms = pos + 2 * S * DP;                 // [S][MP]
+
+  const int tid = threadIdx.x;
+  const int lv = tid / L, part = tid % L;
+  const int gv = rank * per_cta + lv;
+  const bool owner = lv < per_cta && gv < s;
+  const int slot = owner ? gv : 0;
+  const Physics<T> ph = a.ph;
+
+  T x[D], fprev[D], E[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    x[k] = (T)a.init_aos[(int64_t)slot * D + k];
+    fprev[k] = (T)0;
+    E[k] = (T)0;
+  }
+  const T ci = a.mass[slot];
+  const T ci_repel = ci * ph.repel;
+  const int eb = owner ? a.e_begin[slot] : 0;
+  const int ee = owner ? a.e_end[slot] : 0;
+  int ej[2] = {0, 0};
+  T ew[2] = {(T)0, (T)0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int e = eb + part + q * L;
+    if (e < ee) {
+      ej[q] = a.e_idx[e];
+      ew[q] = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+    }
+  }
+  for (int i = tid; i < 2 * S * DP + S * MP; i += blockDim.x) pos[i] = (T)0;
+  __syncthreads();
+  for (int i = tid; i < s; i += blockDim.x) {  // every CTA loads the whole graph's state
+#pragma unroll
+    for (int k = 0; k < D; ++k) pos[i * DP + k] = (T)a.init_aos[(int64_t)i * D + k];
+    const T c = a.mass[i];
+    ms[i * MP] = c;
+    if (NM > 1) ms[i * MP + (NM > 1 ? 1 : 0)] = (T)1.5 * c;
+    if (NM > 2) ms[i * MP + (NM > 2 ? 2 : 0)] = (T)1.875 * c;
+  }
+  cluster.sync();  // also: nobody writes into a peer's shared memory before it is initialised
+
+  const T* pc = pos;
+  T* pn = pos + S * DP;
+  int nxt = 1;
+  for (int it = 0; it < a.iters; ++it) {
+    T f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = (T)0;
+    if (owner) {
+      for (int j0 = part; j0 < S; j0 += L * U) {
+        T d[U][D], r2[U], s3[U], m0[U], m1[U], m2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * L;
+          T xj[D];
+          C::pos(pc, j, xj);
+          C::mass(ms, j, m0[u], m1[u], m2[u]);
+          r2[u] = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[u][k] = x[k] - xj[k];
+            r2[u] = fma(d[u][k], d[u][k], r2[u]);
+          }
+          r2[u] = Real<T>::clamp_lo(r2[u], ph.eps2);
+        }
+        Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2, s3);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) f[k] = fma(d[u][k], s3[u], f[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (eb + part + q * L < ee) {
+          T xj[D], d[D];
+          C::pos(pc, ej[q], xj);
+          T r2 = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[k] = xj[k] - x[k];
+            r2 = fma(d[k], d[k], r2);
+          }
+          const T g = attraction_factor<T, GA>(r2, ew[q], ci, ph);
+#pragma unroll
+          for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+        }
+      }
+      for (int e = eb + part + 2 * L; e < ee; e += L) {
+        const int j = a.e_idx[e];
+        const T w = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+        T xj[D], d[D];
+        C::pos(pc, j, xj);
+        T r2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          d[k] = xj[k] - x[k];
+          r2 = fma(d[k], d[k], r2);
+        }
+        const T g = attraction_factor<T, GA>(r2, w, ci, ph);
+#pragma unroll
+        for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+      }
+    }
+#pragma unroll
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
+    }
+    vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
+    if (owner) {  // the L lanes of the group share out the csize peer stores
+      for (int rr = part; rr < csize; rr += L) {
+        T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[k] = x[k];
+      }
+    }
+    cluster.sync();
+    const T* tmp = pc;
+    pc = pn;
+    pn = const_cast<T*>(tmp);
+    nxt ^= 1;
+  }
+
+  if (!a.normalize) {
+    if (owner && part == 0) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.out_aos[(int64_t)gv * D + k] = (double)x[k];
+    }
+    return;
+  }
+  if (rank != 0) return;  // include/forceatlas.hpp:272-303 by CTA 0 (every CTA holds all positions)
+  auto block_reduce = [&](double val, bool is_max) -> double {
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, val, off);
+      val = is_max ? fmax(val, o) : val + o;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid < 32) {
+      double w = (tid < (int)((blockDim.x + 31) >> 5)) ? red[tid] : 0.0;
+      for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, w, off);
+        w = is_max ? fmax(w, o) : w + o;
+      }
+      if (tid == 0) red[0] = w;
+    }
+    __syncthreads();
+    const double out = red[0];
+    __syncthreads();
+    return out;
+  };
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double part_sum = 0.0;
+    for (int i = tid; i < s; i += blockDim.x) part_sum += (double)pc[i * DP + k];
+    const double tot = block_reduce(part_sum, false);
+    if (tid == 0) bc[k] = tot / s;
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int i = tid; i < s; i += blockDim.x) {
+    double m2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = (double)pc[i * DP + k] - bc[k];
+      m2 += c * c;
+    }
+    mx = fmax(mx, sqrt(m2));
+  }
+  const double maxlen = block_reduce(mx, true);
+  for (int i = tid; i < s; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      a.out_aos[(int64_t)i * D + k] = ((double)pc[i * DP + k] - bc[k]) / maxlen;
   }
 }
 
@@ -341,9 +613,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_onchip_warp(const OnchipA
 }
 
 template <typename T>
-size_t cta_smem(int dim, int max_size) {
-  const int S = (max_size + 1) & ~1;
-  return (size_t)(2 * dim + Real<T>::kMassArrays) * S * sizeof(T);
+size_t cta_smem(int dim, int max_size, int lanes, bool big) {
+  const int S = onchip_spad(max_size, lanes, big ? 2 : 4);
+  const int DP = dim == 2 ? 2 : 4, MP = sizeof(T) == 8 ? 4 : 1;
+  return (size_t)(2 * DP + MP) * S * sizeof(T);
 }
 
 }  // namespace
@@ -371,8 +644,8 @@ template <typename T>
 void launch_onchip_cta(ge_context* ctx, const OnchipArgs<T>& a, int ntasks, int dim, bool ml,
                        int lanes, int threads, int max_size) {
   if (ntasks == 0) return;
-  const size_t smem = cta_smem<T>(dim, max_size);
   const bool big = threads > 512, ga = a.ph.general_attraction != 0;
+  const size_t smem = cta_smem<T>(dim, max_size, lanes, big);
   const void* fn = dim == 2 ? (ml ? cta_kernel<T, 2, true>(lanes, big, ga) : cta_kernel<T, 2, false>(lanes, big, ga))
                             : (ml ? cta_kernel<T, 3, true>(lanes, big, ga) : cta_kernel<T, 3, false>(lanes, big, ga));
   if (smem > 48 * 1024)
@@ -391,6 +664,54 @@ void launch_onchip_warp(ge_context* ctx, const OnchipArgs<T>& a, int npacks, int
   else
     k_onchip_warp<T, 3><<<ctas, kWarpsPerCta * 32, 0, ctx->stream>>>(a, npacks);
   GE_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+namespace {
+template <typename T, int D, bool GA>
+const void* cluster_kernel(int L) {
+  switch (L) {
+    case 1: return (const void*)k_onchip_cluster<T, D, 1, GA>;
+    case 2: return (const void*)k_onchip_cluster<T, D, 2, GA>;
+    case 4: return (const void*)k_onchip_cluster<T, D, 4, GA>;
+    case 8: return (const void*)k_onchip_cluster<T, D, 8, GA>;
+    case 16: return (const void*)k_onchip_cluster<T, D, 16, GA>;
+    default: return (const void*)k_onchip_cluster<T, D, 32, GA>;
+  }
+}
+}  // namespace
+
+// The whole flat problem on one cluster of `csize` CTAs (slot == vertex id).
+template <typename T>
+void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int dim, int csize) {
+  const int per_cta = (n + csize - 1) / csize;
+  // measured (tools/profile_small.py k3sweep): with the vertices spread over several SMs the
+  // widest lane group that fits wins (n = 108: 8 CTAs x 32 lanes 1.5 us/iteration vs 3.3 us on one CTA)
+  int L = 1;
+  while (L < 32 && per_cta * (L * 2) <= 512) L *= 2;
+  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::atoi(v);
+  const int threads = (int)round_up((int64_t)per_cta * L, 32);
+  GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");
+  const bool ga = a.ph.general_attraction != 0;
+  const void* fn = dim == 2 ? (ga ? cluster_kernel<T, 2, true>(L) : cluster_kernel<T, 2, false>(L))
+                            : (ga ? cluster_kernel<T, 3, true>(L) : cluster_kernel<T, 3, false>(L));
+  const size_t smem = cta_smem<T>(dim, n, L, false);
+  if (smem > 48 * 1024)
+    GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[] = {(void*)&a, (void*)&per_cta};
+  GE_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches++;
 }
 
@@ -467,7 +788,17 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   a.forces_only = forces_only ? 1 : 0;
   a.normalize = p.normalize;
   a.ph = make_physics<T>(p);
-  launch_onchip_cta<T>(ctx, a, 1, dim, false, L, threads, n);
+  // Larger coarsest levels are spread over a thread-block cluster (measured crossover n ~ 40).
+  int csize = 1;
+  if (!forces_only) {
+    csize = n >= 80 ? 8 : n >= 40 ? 4 : 1;
+    if (const char* v = std::getenv("GE_CLUSTER")) csize = std::atoi(v);
+    csize = std::max(1, std::min(csize, 8));
+  }
+  if (csize > 1)
+    launch_onchip_cluster<T>(ctx, a, n, dim, csize);
+  else
+    launch_onchip_cta<T>(ctx, a, 1, dim, false, L, threads, n);
   d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
 }

@@ -130,6 +130,16 @@ ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_cs
                                    const double* init, double* coords, int dim,
                                    const ge_params* p);
 
+/* The same for the aggregates [agg_begin, agg_end) only (multi-GPU: aggregates are independent,
+ * include/forceatlas.hpp:340-341, so ranks take disjoint ranges and exchange the level's output
+ * once).  Rows of `coords` that belong to other aggregates are set to 0, so the exchange can be a
+ * sum (x + 0 is exact). */
+ge_status ge_multilevel_forceatlas_shard(ge_context* ctx, const ge_csr* A, const ge_csr* P_T,
+                                         const int32_t* v_A, const double* coords_A,
+                                         const double* r_A, const double* init, double* coords,
+                                         int dim, const ge_params* p, int32_t agg_begin,
+                                         int32_t agg_end);
+
 /* partition::embed(As, P_Ts, d)  src/embed.cpp:561-574, i.e. the embedMultilevel recursion of
  * :576-796: coarsest level flat solve, then per level radii + rescale (:615-777, host) and the
  * per-aggregate solve + prolongation.  As: n_levels + 1 matrices, P_Ts: n_levels.

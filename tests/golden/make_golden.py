@@ -66,7 +66,18 @@ def main():
     x, _ = O.ref_embed(As, Ps, 2, seed=21, nthreads=1)
     out["embed_d2_seed21"] = x
     np.savez_compressed(os.path.join(HERE, "hier_grid30.npz"), **out)
-    for f in ("flat_grid12.npz", "hier_grid30.npz"):
+    # ---- BASELINE config 1: 100 x 100 grid, coarsening 0.25, d = 2, the reference's own partition ---
+    A = G.grid2d(100, 100)
+    Ps = O.ref_partition(A, 0.25, matching_iterations=2, nthreads=1)
+    As = G.hierarchy_from(A, Ps)
+    out = {"L": np.int32(len(Ps))}
+    for l, P in enumerate(Ps):
+        out["P%d_indptr" % l], out["P%d_indices" % l] = P.indptr.astype(np.int32), P.indices.astype(np.int32)
+    x, secs = O.ref_embed(As, Ps, 2, seed=3, nthreads=1)
+    out["embed_d2_seed3"] = x.astype(np.float32)   # statistics only: single precision keeps the file small
+    out["ref_embed_seconds_1thread"] = np.float64(secs)
+    np.savez_compressed(os.path.join(HERE, "config1_grid100.npz"), **out)
+    for f in ("flat_grid12.npz", "hier_grid30.npz", "config1_grid100.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -32,6 +32,19 @@ def load_hier_golden():
     return As, Ps, z
 
 
+def load_config1_golden(graphs):
+    """BASELINE config 1 (grid 100x100, coarsening 0.25): hierarchy from the reference's own
+    partitioner + the compiled reference's embed() output for seed 3."""
+    z = np.load(os.path.join(GOLDEN, "config1_grid100.npz"))
+    A = graphs.grid2d(100, 100)
+    Ps, n = [], A.shape[0]
+    for l in range(int(z["L"])):
+        ptr, idx = z["P%d_indptr" % l], z["P%d_indices" % l]
+        Ps.append(sp.csr_matrix((np.ones(len(idx)), idx, ptr), shape=(len(ptr) - 1, n)))
+        n = len(ptr) - 1
+    return graphs.hierarchy_from(A, Ps), Ps, z
+
+
 def force_error(F, F_ref, scale):
     """Per-vertex |F - F_ref|_2 divided by the conditioning scale the oracle reports (the sum of
     the norms of the individual terms that were added into that vertex's force)."""

@@ -99,11 +99,18 @@ def test_positions_after_k_iterations(ctx, capi, oracle, k, path, monkeypatch):
 
 
 def test_normalize_option(ctx, capi, oracle, monkeypatch):
+    """normalize=true epilogue (include/forceatlas.hpp:272-303) on every flat path (tiled, single
+    CTA, cluster); 7 iterations, bound = the oracle's own sensitivity to a 1-ulp input change."""
     A, z = load_flat_golden()
-    for path in ("0", "1024"):
-        monkeypatch.setenv("GE_ONCHIP_MAX", path)
-        x = ctx.flat_forceatlas(A, 2, z["x0_d2"], capi.flat_params(iterations=7, normalize=1))
-        assert np.abs(x - z["x_d2_k7_normalize"]).max() < 1e-10
+    x0, ref = z["x0_d2"], z["x_d2_k7_normalize"]
+    sign = np.random.default_rng(0).choice([-1.0, 1.0], size=x0.shape)
+    pert, _ = oracle.flat_run(A, 2, x0 * (1 + sign * 2.2e-16), oracle.Params(iterations=7, normalize=True))
+    tol = max(1e-10, 50 * np.abs(pert - ref).max())
+    for onchip_max, cluster in (("0", "1"), ("1024", "1"), ("1024", "8")):
+        monkeypatch.setenv("GE_ONCHIP_MAX", onchip_max)
+        monkeypatch.setenv("GE_CLUSTER", cluster)
+        x = ctx.flat_forceatlas(A, 2, x0, capi.flat_params(iterations=7, normalize=1))
+        assert np.abs(x - ref).max() < tol, (onchip_max, cluster, np.abs(x - ref).max(), tol)
         assert abs(np.linalg.norm(x, axis=1).max() - 1.0) < 1e-12
 
 
@@ -157,3 +164,22 @@ def test_full_size_properties(ctx, capi, oracle, graphs):
     for r in rows:
         F_ref, S = oracle.flat_forces(A, 2, x0, rows=(int(r), int(r) + 1))
         assert np.linalg.norm(F[r] - F_ref[r]) / S[r] < TOL_F64
+
+
+@pytest.mark.parametrize("csize", [2, 4, 8])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cluster_solve_matches_single_cta(ctx, capi, oracle, csize, dim, monkeypatch):
+    """The thread-block-cluster variant of the coarsest-level solve (DSMEM position exchange) gives
+    the positions of the single-CTA kernel: same arithmetic per vertex, only the placement differs,
+    so the results are bit-identical; both are within the chaos-aware bound of the golden
+    reference positions."""
+    A, z = load_flat_golden()
+    monkeypatch.setenv("GE_ONCHIP_MAX", "1024")
+    monkeypatch.setenv("GE_ONCHIP_LANES", "4")  # same lane count -> same summation order
+    x0 = z["x0_d%d" % dim]
+    for k in (1, 25):
+        monkeypatch.setenv("GE_CLUSTER", "1")
+        x1 = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k))
+        monkeypatch.setenv("GE_CLUSTER", str(csize))
+        xc = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k))
+        assert np.array_equal(x1, xc), np.abs(x1 - xc).max()

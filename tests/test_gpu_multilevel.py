@@ -163,3 +163,47 @@ def test_config2_full_size_properties(ctx, capi, graphs):
     spread = np.linalg.norm(x - cent[v_A], axis=1).mean()
     extent = np.linalg.norm(x - x.mean(0), axis=1).max()
     assert spread < 0.05 * extent
+
+
+def test_sharded_aggregates_equal_unsharded(ctx, capi, oracle, graphs):
+    """ge_multilevel_forceatlas_shard over two aggregate ranges, summed, is bit-identical to the
+    unsharded call (aggregates are independent, include/forceatlas.hpp:340-341); and the sharded
+    embed driver equals ge_embed for the same seed."""
+    from graph_embed_b200 import sharding
+    As, Ps = _case(graphs, "rmat")
+    A, P = As[0], Ps[0]
+    m = P.shape[0]
+    rng = np.random.default_rng(2)
+    cA, rA = rng.normal(size=(m, 2)), rng.random(m) * 0.3 + 0.05
+    init = oracle.multilevel_init(P, 2, 5)
+    p = capi.multilevel_params(iterations=20)
+    full = ctx.multilevel_forceatlas(A, P, cA, rA, 2, p, init=init)
+    blocks = sharding.aggregate_blocks(A, P, 3)
+    parts = [ctx.multilevel_forceatlas(A, P, cA, rA, 2, p, init=init, aggregates=b) for b in blocks]
+    assert np.array_equal(sum(parts), full)
+    v_A = capi.vertex_to_aggregate(P)
+    for b, part in zip(blocks, parts):
+        foreign = (v_A < b[0]) | (v_A >= b[1])
+        assert not part[foreign].any()
+
+    class OneRank:  # the driver's collective is a no-op at world size 1
+        @staticmethod
+        def all_reduce(t):
+            return t
+    x1 = sharding.embed_sharded(ctx, OneRank, As, Ps, 2, seed=7, rank=0, world=1, coarse_iterations=200)
+    x2, _ = ctx.embed(As, Ps, 2, seed=7, coarse_iterations=200)
+    assert np.array_equal(x1, x2)
+
+
+def test_config1_embed_against_reference(ctx, capi, graphs):
+    """BASELINE config 1 at full size: 100 x 100 grid, the hierarchy the reference's partitioner
+    builds (10000 -> 1270 -> 209 -> 43 -> 34), d = 2, 100 000 coarsest iterations.  Layout statistics
+    against the compiled reference's own embed() output (golden)."""
+    from helpers import load_config1_golden
+    As, Ps, z = load_config1_golden(graphs)
+    assert [A.shape[0] for A in As] == [10000, 1270, 209, 43, 34]
+    x, st = ctx.embed(As, Ps, 2, seed=3)
+    assert np.isfinite(x).all()
+    s1, s2 = layout_stats(As[0], x), layout_stats(As[0], z["embed_d2_seed3"].astype(np.float64))
+    for key in s1:
+        assert abs(s1[key] - s2[key]) < 0.25 * abs(s2[key]), (key, s1, s2)

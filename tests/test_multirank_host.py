@@ -83,3 +83,50 @@ def test_row_block_partition_covers_every_row():
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(b[1] == c[0] for b, c in zip(blocks, blocks[1:]))
             assert all(b[2] * world == b[3] and b[3] % 256 == 0 for b in blocks)
+
+
+def test_aggregate_blocks_partition(graphs):
+    from graph_embed_b200 import sharding
+    As, Ps = graphs.coarsen(graphs.rmat(11, 8, seed=3), 0.25, min_coarse=30)
+    for world in (1, 2, 4, 8):
+        blocks = sharding.aggregate_blocks(As[0], Ps[0], world)
+        assert blocks[0][0] == 0 and blocks[-1][1] == Ps[0].shape[0]
+        assert all(b[1] == c[0] and b[0] <= b[1] for b, c in zip(blocks, blocks[1:]))
+        s = np.diff(Ps[0].indptr).astype(float)
+        cost = np.array([(s[b:e] ** 2).sum() for b, e in blocks])
+        if world > 1:  # no rank carries more than its share plus the largest single aggregate
+            assert cost.max() <= (s ** 2).sum() / world + (s ** 2).max() * 1.5 + Ps[0].shape[1]
+
+
+def _sum_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest  # noqa: F401
+    from graph_embed_b200 import graphs, sharding
+    O = conftest.ORACLE
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    As, Ps = graphs.coarsen(graphs.grid2d(14, 14), 0.25, min_coarse=10)
+    A, P = As[0], Ps[0]
+    m = P.shape[0]
+    rng = np.random.default_rng(0)
+    cA, rA = rng.normal(size=(m, 2)), rng.random(m) + 0.1
+    full = O.multilevel_run(A, P, cA, rA, 2, O.multilevel_init(P, 2, 3), O.Params(iterations=10))
+    b, e = sharding.aggregate_blocks(A, P, world)[rank]
+    mine = np.zeros_like(full)            # what ge_multilevel_forceatlas_shard returns: own rows, zeros elsewhere
+    rows = P.indices[P.indptr[b]:P.indptr[e]]
+    mine[rows] = full[rows]
+    t = torch.from_numpy(mine)
+    dist.all_reduce(t)
+    if rank == 0:
+        np.save(out, np.stack([t.numpy(), full]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_level_output_exchange_is_exact(tmp_path):
+    """Sharded aggregates + one sum all-reduce of the level output == the unsharded level."""
+    out = str(tmp_path / "lvl.npy")
+    mp.spawn(_sum_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got, full = np.load(out)
+    assert np.array_equal(got, full)

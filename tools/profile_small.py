@@ -37,17 +37,18 @@ elif mode == "k3sweep":
         Ac = As[-1]
         n = Ac.shape[0]
         x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
-        for L in (1, 2, 4, 8, 16, 32):
-            if n * L > 1024:
+        for cs, L in ((1, 8), (2, 8), (4, 8), (8, 8), (2, 16), (4, 16), (8, 16), (8, 32), (4, 4), (8, 4)):
+            if (n + cs - 1) // cs * L > (1024 if cs == 1 else 512):
                 continue
             os.environ["GE_ONCHIP_LANES"] = str(L)
+            os.environ["GE_CLUSTER"] = str(cs)
             ts = []
             for iters in (1, 20001):
                 ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters, precision=prec))
                 t = time.time()
                 ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters, precision=prec))
                 ts.append(time.time() - t)
-            print("n=%d nnz=%d L=%d: %.3f us/iter (overhead %.2f ms)" % (n, Ac.nnz, L, 1e6 * (ts[1] - ts[0]) / 20000, 1e3 * ts[0]), flush=True)
+            print("n=%d nnz=%d cluster=%d L=%d: %.3f us/iter (overhead %.2f ms)" % (n, Ac.nnz, cs, L, 1e6 * (ts[1] - ts[0]) / 20000, 1e3 * ts[0]), flush=True)
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     prec = capi.GE_F32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else capi.GE_F64
