@@ -249,6 +249,57 @@ __global__ void __launch_bounds__(256) k_repulsion_fixup(const RepArgs<T> a, int
   }
 }
 
+// One neighbour's coordinates from the interleaved copy (vector loads; DP = 2 or 4 reals).
+template <typename T, int D>
+struct Gather;
+template <>
+struct Gather<double, 2> {
+  static constexpr int DP = 2;
+  __device__ __forceinline__ static void ld(const double* b, int j, double (&x)[2]) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(b) + j);
+    x[0] = v.x;
+    x[1] = v.y;
+  }
+};
+template <>
+struct Gather<double, 3> {
+  static constexpr int DP = 4;
+  __device__ __forceinline__ static void ld(const double* b, int j, double (&x)[3]) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(b) + 2 * j);
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = __ldg(b + 4 * j + 2);
+  }
+};
+template <>
+struct Gather<float, 2> {
+  static constexpr int DP = 2;
+  __device__ __forceinline__ static void ld(const float* b, int j, float (&x)[2]) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(b) + j);
+    x[0] = v.x;
+    x[1] = v.y;
+  }
+};
+template <>
+struct Gather<float, 3> {
+  static constexpr int DP = 4;
+  __device__ __forceinline__ static void ld(const float* b, int j, float (&x)[3]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(b) + j);
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = v.z;
+  }
+};
+
+template <typename T, int D>
+__global__ void k_soa_to_gather(const T* __restrict__ soa, int64_t ld, T* __restrict__ aos) {
+  constexpr int DP = Gather<T, D>::DP;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+#pragma unroll
+  for (int k = 0; k < DP; ++k) aos[i * DP + k] = k < D ? soa[(int64_t)k * ld + i] : (T)0;
+}
+
 // K1b+c.  G lanes cooperate on one row (G = 4..32 chosen from the average degree); lane 0 of the
 // group finishes the row: adds the repulsion sum, gravity, derives the per-vertex speed and
 // writes the moved position into the NEXT coordinate buffer (Jacobi: everybody still reads the
@@ -286,10 +337,20 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
     const T wb = (weighted && two) ? a.W[eb] : (T)1;
     T da[D], db[D];
     T r2a = (T)0, r2b = (T)0;
+    if (a.aos_cur != nullptr) {
+      Gather<T, D>::ld(a.aos_cur, ja, da);
+      Gather<T, D>::ld(a.aos_cur, jb, db);
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      da[k] = a.pos_cur[(int64_t)k * a.ld + ja] - x[k];
-      db[k] = a.pos_cur[(int64_t)k * a.ld + jb] - x[k];
+      for (int k = 0; k < D; ++k) {
+        da[k] -= x[k];
+        db[k] -= x[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        da[k] = a.pos_cur[(int64_t)k * a.ld + ja] - x[k];
+        db[k] = a.pos_cur[(int64_t)k * a.ld + jb] - x[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -314,6 +375,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
     for (int k = 0; k < D; ++k) {
       a.Fprev[(int64_t)k * a.ldf + r] = fprev[k];
       if (a.update) a.pos_next[(int64_t)k * a.ld + i] = x[k];
+    }
+    if (a.update && a.aos_next != nullptr) {
+      constexpr int DP = Gather<T, D>::DP;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) a.aos_next[(int64_t)i * DP + k] = k < D ? x[k] : (T)0;
     }
   }
 }
@@ -503,10 +569,12 @@ template class RepulsionPlan<float>;
 namespace {
 template <typename T, int D, bool ML, bool GA>
 void launch_step_g(ge_context* ctx, const StepArgs<T>& a, int group) {
-  const int g = group <= 4 ? 4 : group <= 8 ? 8 : group <= 16 ? 16 : 32;
+  const int g = group <= 1 ? 1 : group <= 2 ? 2 : group <= 4 ? 4 : group <= 8 ? 8 : group <= 16 ? 16 : 32;
   const int64_t threads = (int64_t)a.nrows * g;
   const unsigned grid = (unsigned)((threads + 255) / 256);
-  if (g == 4) k_attract_step<T, D, 4, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  if (g == 1) k_attract_step<T, D, 1, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (g == 2) k_attract_step<T, D, 2, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (g == 4) k_attract_step<T, D, 4, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
   else if (g == 8) k_attract_step<T, D, 8, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
   else if (g == 16) k_attract_step<T, D, 16, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
   else k_attract_step<T, D, 32, ML, GA><<<grid, 256, 0, ctx->stream>>>(a);
@@ -536,7 +604,9 @@ template void launch_attract_step<double>(ge_context*, const StepArgs<double>&, 
 template void launch_attract_step<float>(ge_context*, const StepArgs<float>&, int, int, bool);
 
 int group_for_degree(double avg_deg) {
-  return avg_deg <= 6 ? 4 : avg_deg <= 12 ? 8 : avg_deg <= 24 ? 16 : 32;
+  // measured on B200 (n = 2M, avg degree 10, d = 3): 2 lanes per row 0.244 ms, 1: 0.269, 4: 0.283,
+  // 8: 0.40 -- short rows want few lanes (the per-row epilogue runs on one lane of the group)
+  return avg_deg <= 16 ? 2 : avg_deg <= 32 ? 4 : avg_deg <= 64 ? 8 : avg_deg <= 128 ? 16 : 32;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -594,6 +664,8 @@ class FlatSolverT final : public FlatSolver {
     }
     avg_deg_ = nrows_ > 0 ? double(lnnz) / nrows_ : 0.0;
 
+    aos_[0].alloc(ctx, (size_t)gather_dp() * ld_);
+    aos_[1].alloc(ctx, (size_t)gather_dp() * ld_);
     own0_.alloc(ctx, (size_t)dim_ * ld_);
     own1_.alloc(ctx, (size_t)dim_ * ld_);
     own0_.zero(ctx->stream);
@@ -623,6 +695,7 @@ class FlatSolverT final : public FlatSolver {
     GE_CUDA(cudaMemsetAsync(b0, 0, (size_t)dim_ * ld_ * sizeof(T), ctx->stream));
     GE_CUDA(cudaMemsetAsync(b1, 0, (size_t)dim_ * ld_ * sizeof(T), ctx->stream));
     cur_ = 0;
+    aos_valid_ = stepped_ = false;
   }
   void upload_coords(const double* aos) override {
     stage_.upload(ctx, aos, (size_t)n_ * dim_);
@@ -634,6 +707,7 @@ class FlatSolverT final : public FlatSolver {
     GE_CUDA(cudaMemcpyAsync(buf_[cur_ ^ 1], buf_[cur_], (size_t)total * sizeof(T),
                             cudaMemcpyDeviceToDevice, ctx->stream));
     Fprev_.zero(ctx->stream);
+    aos_valid_ = stepped_ = false;
   }
   void download_coords(double* aos) override {
     const int64_t total = (int64_t)n_ * dim_;
@@ -653,9 +727,20 @@ class FlatSolverT final : public FlatSolver {
     stage_.download(ctx, aos, (size_t)total);
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  int gather_dp() const { return dim_ == 2 ? 2 : 4; }
+  void refresh_gather_copy() {
+    const unsigned grid = (unsigned)((ld_ + 255) / 256);
+    if (dim_ == 2) k_soa_to_gather<T, 2><<<grid, 256, 0, ctx->stream>>>(buf_[cur_], ld_, aos_[cur_].get());
+    else k_soa_to_gather<T, 3><<<grid, 256, 0, ctx->stream>>>(buf_[cur_], ld_, aos_[cur_].get());
+    ctx->launches++;
+  }
   void* cur_coords() override { return buf_[cur_]; }
   void* next_coords() override { return buf_[cur_ ^ 1]; }
-  void swap() override { cur_ ^= 1; }
+  void swap() override {
+    cur_ ^= 1;
+    aos_valid_ = stepped_;  // the step kernel just wrote the owned rows of the new current copy
+    stepped_ = false;
+  }
 
   void launch_iteration(bool update) override {
     if (nrows_ == 0) return;
@@ -670,6 +755,13 @@ class FlatSolverT final : public FlatSolver {
     sa.W = W_.size() ? W_.get() : nullptr;
     sa.pos_cur = buf_[cur_];
     sa.pos_next = buf_[cur_ ^ 1];
+    if (use_gather_copy_) {
+      // The copy of the current buffer is exact when this plan wrote every row of it in the
+      // previous step; otherwise (first step, or rows updated by other ranks) it is rebuilt.
+      if (!(aos_valid_ && nrows_ == n_)) refresh_gather_copy();
+      sa.aos_cur = aos_[cur_].get();
+      sa.aos_next = aos_[cur_ ^ 1].get();
+    }
     sa.Frep = Frep_.get();
     sa.Fprev = Fprev_.get();
     sa.mass = mass_.get();
@@ -680,8 +772,10 @@ class FlatSolverT final : public FlatSolver {
     sa.nrows = nrows_;
     sa.update = update ? 1 : 0;
     sa.ph = ph_;
-    if (kernel_mask_ & 2)
+    if (kernel_mask_ & 2) {
       launch_attract_step<T>(ctx, sa, dim_, env_int("GE_STEP_GROUP", group_for_degree(avg_deg_)), false);
+      stepped_ = update;
+    }
     if (prof_) {
       GE_CUDA(cudaEventRecord(ev_[2], ctx->stream));
       GE_CUDA(cudaEventSynchronize(ev_[2]));
@@ -721,7 +815,9 @@ class FlatSolverT final : public FlatSolver {
   int64_t ld_ = 0, ldf_ = 0;
   Physics<T> ph_;
   double avg_deg_ = 0;
-  DevBuf<T> mass_, own0_, own1_, Frep_, Fprev_, W_;
+  DevBuf<T> mass_, own0_, own1_, Frep_, Fprev_, W_, aos_[2];
+  bool use_gather_copy_ = std::getenv("GE_NO_GATHER_COPY") == nullptr;
+  bool aos_valid_ = false, stepped_ = false;
   DevBuf<int> rowptr_, J_;
   std::unique_ptr<RepulsionPlan<T>> rep_;
   DevBuf<double> stage_;

@@ -69,6 +69,11 @@ struct StepArgs {
   const T* W;          // nullptr: unit weights
   const T* pos_cur;    // [D][ld]
   T* pos_next;         // [D][ld]
+  // Interleaved copies of the coordinates for the gather side: one 16-byte (d = 2) or 32-byte
+  // (d = 3, padded to 4 reals; FP32: 8 / 16 bytes) record per vertex, so a neighbour costs one
+  // L2 sector instead of one per dimension.  nullptr: gather from the SoA arrays.
+  const T* aos_cur = nullptr;  // [ld][DP]
+  T* aos_next = nullptr;       // [ld][DP]
   const T* Frep;       // [D][ldf] (owned rows)
   T* Fprev;            // [D][ldf]
   const T* mass;       // [ld]
