@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
               d[t][k] = xi[t][k] - xj[k][v];
               r2[t] = fma(d[t][k], d[t][k], r2[t]);
             }
-            r2[t] = Real<T>::clamp_lo(r2[t], a.eps2);
           }
+          Real<T>::template clamp_lo_n<IPT>(r2, a.eps2);
           Real<T>::template inv_cube_mass_n<IPT>(r2, mj[0][v], mj[NM > 1 ? 1 : 0][v],
                                                  mj[NM > 2 ? 2 : 0][v], s3);
 #pragma unroll
