@@ -1,0 +1,66 @@
+"""One-off full-size runs of the BASELINE configs through ge_embed (single GPU):
+  python tools/run_config.py config3 | config5 [n_points] | config2 | config1
+Prints one JSON line: hierarchy shape, embed() wall time, per-phase times, properties."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry
+
+entry.load_package()
+from graph_embed_b200 import capi, graphs
+
+
+def build(name, arg):
+    if name == "config1":
+        return graphs.grid2d(100, 100), 0.25, 2
+    if name == "config2":
+        return graphs.rgg(100_000, 10.0, seed=12345), 0.25, 2
+    if name == "config3":
+        return graphs.rmat(int(arg or 20), 16, seed=1), 0.25, 3
+    if name == "config5":
+        return graphs.delaunay3d(int(arg or 4_000_000), seed=1), 0.125, 3
+    raise SystemExit("unknown config")
+
+
+def main():
+    name = sys.argv[1]
+    arg = sys.argv[2] if len(sys.argv) > 2 else None
+    t = time.time()
+    A, cf, dim = build(name, arg)
+    t_gen = time.time() - t
+    t = time.time()
+    As, Ps = graphs.coarsen(A, cf, min_coarse=64)
+    t_coarsen = time.time() - t
+    stats = graphs.level_stats(As, Ps)
+    ctx = capi.Context(0)
+    ctx.embed(As[-2:], Ps[-1:], dim, seed=1, coarse_iterations=100)  # warm-up (context, pool)
+    walls = []
+    for rep in range(2):
+        t = time.time()
+        x, st = ctx.embed(As, Ps, dim, seed=1 + rep)
+        walls.append(time.time() - t)
+    v_A = capi.vertex_to_aggregate(Ps[0])
+    cent = np.zeros((Ps[0].shape[0], dim))
+    np.add.at(cent, v_A, x)
+    cent /= np.diff(Ps[0].indptr)[:, None]
+    spread = float(np.linalg.norm(x - cent[v_A], axis=1).mean())
+    extent = float(np.linalg.norm(x - x.mean(0), axis=1).max())
+    out = {"config": name, "n": A.shape[0], "nnz": int(A.nnz), "dim": dim, "coarsening": cf,
+           "levels": [s["n"] for s in stats], "max_aggregate": [s["max_size"] for s in stats],
+           "pairs_per_iteration": [s["pairs"] for s in stats],
+           "embed_wall_s": min(walls), "coarse_ms": st["coarse_ms"], "levels_ms": st["levels_ms"],
+           "host_radii_ms": st["host_radii_ms"], "kernel_launches": st["kernel_launches"],
+           "pair_interactions": st["pair_interactions"], "edge_visits": st["edge_visits"],
+           "finite": bool(np.isfinite(x).all()), "aggregate_spread_over_extent": spread / extent,
+           "host_generate_s": t_gen, "host_coarsen_s": t_coarsen}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
