@@ -12,7 +12,9 @@
 #include <cstring>
 #include <memory>
 #include <random>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -151,24 +153,49 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
   std::vector<int> parent(m, -1);  // :684
   for (int b = 0; b < mc; ++b)
     for (int c = PI[b]; c < PI[b + 1]; ++c) parent[PJ[c]] = b;
-  std::vector<Event> ev;
-  for (int b = 0; b < mc; ++b) {  // :686-756 (independent per super-aggregate)
-    const int s = PI[b + 1] - PI[b];
-    if (s == 1) {
-      r_A[PJ[PI[b]]] = r_Ac[b];
-      continue;
-    }
-    ev.clear();
-    for (int c = PI[b]; c < PI[b + 1]; ++c) local[PJ[c]] = c - PI[b];
-    for (int c = PI[b]; c < PI[b + 1]; ++c) {
-      const int a = PJ[c];
-      for (int kk = A_c->indptr[a]; kk < A_c->indptr[a + 1]; ++kk) {
-        const int j = A_c->indices[kk];
-        if (a < j && parent[j] == parent[a])
-          ev.push_back(Event{-dist(coords_A + (size_t)a * dim, coords_A + (size_t)j * dim, dim) / 2, a, j});
+  // :686-756: the families are independent (the reference runs this loop under `omp parallel
+  // for`, src/embed.cpp:685); here a few host threads pull blocks of families off a counter.
+  auto families = [&](int b0, int b1, std::vector<int>& loc) {
+    std::vector<Event> ev;
+    std::vector<int> ip, in, vr;
+    std::vector<HeapItem> hp;
+    for (int b = b0; b < b1; ++b) {
+      const int s = PI[b + 1] - PI[b];
+      if (s == 1) {
+        r_A[PJ[PI[b]]] = r_Ac[b];
+        continue;
       }
+      ev.clear();
+      for (int c = PI[b]; c < PI[b + 1]; ++c) loc[PJ[c]] = c - PI[b];
+      for (int c = PI[b]; c < PI[b + 1]; ++c) {
+        const int a = PJ[c];
+        for (int kk = A_c->indptr[a]; kk < A_c->indptr[a + 1]; ++kk) {
+          const int j = A_c->indices[kk];
+          if (a < j && parent[j] == parent[a])
+            ev.push_back(Event{-dist(coords_A + (size_t)a * dim, coords_A + (size_t)j * dim, dim) / 2, a, j});
+        }
+      }
+      grow_balls(ev, r_A, m, loc.data(), s, ip, in, vr, hp);
     }
-    grow_balls(ev, r_A, m, local.data(), s, inc_ptr, inc, ver, heap);
+  };
+  const int kBlock = 512;
+  const int nthreads = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u,
+                                                   (unsigned)((mc + kBlock - 1) / kBlock)}));
+  if (nthreads <= 1) {
+    families(0, mc, local);
+  } else {
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&] {
+        std::vector<int> loc(std::max(m, 1));
+        for (;;) {
+          const int b0 = next.fetch_add(kBlock);
+          if (b0 >= mc) break;
+          families(b0, std::min(mc, b0 + kBlock), loc);
+        }
+      });
+    for (auto& th : pool) th.join();
   }
   for (int b = 0; b < mc; ++b) {  // :757-777 shrink each family into its parent ball
     const double* cb = coords_Ac + (size_t)b * dim;

@@ -207,3 +207,41 @@ def test_config1_embed_against_reference(ctx, capi, graphs):
     s1, s2 = layout_stats(As[0], x), layout_stats(As[0], z["embed_d2_seed3"].astype(np.float64))
     for key in s1:
         assert abs(s1[key] - s2[key]) < 0.25 * abs(s2[key]), (key, s1, s2)
+
+
+def _embed_properties(ctx, capi, As, Ps, dim):
+    x, st = ctx.embed(As, Ps, dim, seed=1)
+    assert np.isfinite(x).all() and x.shape == (As[0].shape[0], dim)
+    v_A = capi.vertex_to_aggregate(Ps[0])
+    cent = np.zeros((Ps[0].shape[0], dim))
+    np.add.at(cent, v_A, x)
+    cent /= np.diff(Ps[0].indptr)[:, None]
+    spread = np.linalg.norm(x - cent[v_A], axis=1).mean()
+    extent = np.linalg.norm(x - x.mean(0), axis=1).max()
+    assert spread < 0.05 * extent
+    pairs = 100000.0 * As[-1].shape[0] * (As[-1].shape[0] - 1) + 100.0 * sum(
+        float((np.diff(P.indptr).astype(np.int64) * (np.diff(P.indptr) - 1)).sum()) for P in Ps)
+    assert st["pair_interactions"] == pytest.approx(pairs)
+    return x
+
+
+@pytest.mark.parametrize("name", ["rmat16_d3", "delaunay200k_d3"])
+def test_config3_config5_shapes_reduced(ctx, capi, graphs, name):
+    """BASELINE configs 3 (R-MAT, d = 3, coarsening 0.25) and 5 (3-D Delaunay mesh, d = 3,
+    coarsening 0.125) at reduced size; the full sizes run under GE_FULL_CONFIGS=1 below."""
+    if name == "rmat16_d3":
+        As, Ps = graphs.coarsen(graphs.rmat(16, 16, seed=1), 0.25, min_coarse=64)
+    else:
+        As, Ps = graphs.coarsen(graphs.delaunay3d(200_000, seed=1), 0.125, min_coarse=64)
+    _embed_properties(ctx, capi, As, Ps, 3)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GE_FULL_CONFIGS"),
+                    reason="full-size configs 3 / 5 take minutes of host-side graph generation; set GE_FULL_CONFIGS=1")
+@pytest.mark.parametrize("name", ["config3", "config5"])
+def test_config3_config5_full_size(ctx, capi, graphs, name):
+    if name == "config3":   # R-MAT scale 20, edge factor 16, largest component: 646k vertices, 31M entries
+        As, Ps = graphs.coarsen(graphs.rmat(20, 16, seed=1), 0.25, min_coarse=64)
+    else:                   # Delaunay tetrahedralisation of 4M points: ~62M entries
+        As, Ps = graphs.coarsen(graphs.delaunay3d(4_000_000, seed=1), 0.125, min_coarse=64)
+    _embed_properties(ctx, capi, As, Ps, 3)
