@@ -31,10 +31,29 @@ uint32_t resolve_seed(uint32_t seed) {
   return rd();
 }
 
+// uniform_real_distribution<double>(-1,1) over std::mt19937 as libstdc++ evaluates it
+// (generate_canonical<double,53>: two 32-bit draws, low word first, divided by 2^64; then
+// a + (b-a)*u), written out so that it runs at the speed of the raw engine (~3x faster than going
+// through the distribution object); bit-identical to it (tests/test_capi_host.py).
 void reference_uniform(uint32_t seed, int64_t count, double* out) {
   std::mt19937 gen(seed);
-  std::uniform_real_distribution<double> random(-1.0, 1.0);
-  for (int64_t c = 0; c < count; ++c) out[c] = random(gen);
+  for (int64_t c = 0; c < count; ++c) {
+    const double lo = (double)gen();
+    const double hi = (double)gen();
+    double u = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+    if (u >= 1.0) u = std::nextafter(1.0, 0.0);
+    out[c] = u * (1.0 - (-1.0)) + (-1.0);
+  }
+}
+
+// The reference's draw order for the local initial coordinates of one level
+// (include/forceatlas.hpp:341, 356-358): aggregate-major, member-major, k-minor.
+void level_init_stream(uint32_t seed, const ge_csr& P_T, int dim, double* init_by_vertex) {
+  const int64_t n = P_T.indptr[P_T.rows];
+  std::vector<double> stream((size_t)n * dim);
+  reference_uniform(seed, n * dim, stream.data());
+  for (int64_t c = 0; c < n; ++c)
+    for (int k = 0; k < dim; ++k) init_by_vertex[(size_t)P_T.indices[c] * dim + k] = stream[c * dim + k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -339,24 +358,24 @@ struct EmbedRun {
     std::vector<int32_t> v_A(n);  // :605
     for (int a = 0; a < m; ++a)
       for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) v_A[P.indices[c]] = a;
-    // initial local coordinates in the reference's draw order (forceatlas.hpp:341, 356-358)
-    std::vector<double> init((size_t)n * dim);
-    {
-      std::mt19937 gen(resolve_seed(opt.seed));
-      std::uniform_real_distribution<double> random(-1.0, 1.0);
-      for (int a = 0; a < m; ++a)
-        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
-          for (int k = 0; k < dim; ++k) init[(size_t)P.indices[c] * dim + k] = random(gen);
+    // Initial local coordinates: with a fixed seed, the reference's own stream in its draw order
+    // (forceatlas.hpp:341, 356-358); with seed 0 (the reference's std::random_device mode, where
+    // any stream is as good as another) they are drawn on the device.
+    std::vector<double> init;
+    if (opt.seed != 0) {
+      init.resize((size_t)n * dim);
+      level_init_stream(opt.seed, P, dim, init.data());
     }
     ge_params p;
     ge_params_default_multilevel(&p);
     p.iterations = opt.level_iterations;  // :793
     p.precision = opt.precision;
+    p.seed = opt.seed;
     std::vector<double> coords((size_t)n * dim);
     const double t1 = now_ms();
     double pairs = 0.0;
-    multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(), init.data(), coords.data(),
-                     dim, p, false, &pairs);
+    multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(),
+                     init.empty() ? nullptr : init.data(), coords.data(), dim, p, false, &pairs);
     st.levels_ms += now_ms() - t1;
     st.pair_interactions += pairs * p.iterations;
     st.edge_visits += double(A.nnz) * p.iterations;
@@ -504,15 +523,11 @@ ge_status ge_multilevel_forceatlas(ge_context* ctx, const ge_csr* A, const ge_cs
     check_csr(P_T, "P_T");
     GE_REQUIRE(v_A && coords_A && r_A && coords && p, "null argument");
     std::vector<double> drawn;
-    if (init == nullptr) {  // include/forceatlas.hpp:341, 356-358
+    if (init == nullptr && p->seed != 0) {  // include/forceatlas.hpp:341, 356-358
       drawn.resize((size_t)A->rows * dim);
-      std::mt19937 gen(resolve_seed(p->seed));
-      std::uniform_real_distribution<double> random(-1.0, 1.0);
-      for (int a = 0; a < P_T->rows; ++a)
-        for (int c = P_T->indptr[a]; c < P_T->indptr[a + 1]; ++c)
-          for (int k = 0; k < dim; ++k) drawn[(size_t)P_T->indices[c] * dim + k] = random(gen);
+      level_init_stream(p->seed, *P_T, dim, drawn.data());
       init = drawn.data();
-    }
+    }  // seed 0: drawn on the device (the reference's non-reproducible std::random_device mode)
     multilevel_solve(ctx, *A, *P_T, v_A, coords_A, r_A, init, coords, dim, *p, false, nullptr);
   });
 }
@@ -531,11 +546,7 @@ ge_status ge_multilevel_forceatlas_shard(ge_context* ctx, const ge_csr* A, const
     if (init == nullptr) {  // every rank draws the whole level's stream: identical on all ranks
       GE_REQUIRE(p->seed != 0, "sharded solve with init == NULL needs a fixed seed shared by all ranks");
       drawn.resize((size_t)A->rows * dim);
-      std::mt19937 gen(p->seed);
-      std::uniform_real_distribution<double> random(-1.0, 1.0);
-      for (int a = 0; a < P_T->rows; ++a)
-        for (int c = P_T->indptr[a]; c < P_T->indptr[a + 1]; ++c)
-          for (int k = 0; k < dim; ++k) drawn[(size_t)P_T->indices[c] * dim + k] = random(gen);
+      level_init_stream(p->seed, *P_T, dim, drawn.data());
       init = drawn.data();
     }
     multilevel_solve(ctx, *A, *P_T, v_A, coords_A, r_A, init, coords, dim, *p, false, nullptr,

@@ -126,6 +126,7 @@ void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                  const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);
 void reference_uniform(uint32_t seed, int64_t count, double* out);
+void level_init_stream(uint32_t seed, const ge_csr& P_T, int dim, double* init_by_vertex);
 uint32_t resolve_seed(uint32_t seed);
 
 }  // namespace ge

@@ -144,6 +144,18 @@ __global__ void k_ml_singletons(const int* __restrict__ vtx, const int* __restri
   for (int k = 0; k < D; ++k) out[(int64_t)v * D + k] = cA[(int64_t)a * D + k] + rA[a] * c;
 }
 
+// Initial local coordinates U(-1,1) drawn on the device (seed 0 = the reference's
+// std::random_device mode): a counter-based splitmix64 hash of (seed, element index).
+__global__ void k_random_init(double* __restrict__ out, int64_t count, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  out[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
 template <typename T, int D>
 __global__ void k_ml_gather_pos(const double* __restrict__ init, const int* __restrict__ vtx,
                                 int nslots, int64_t ld, T* __restrict__ pos) {
@@ -236,6 +248,15 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
   const bool weighted = p.use_weights && A.data != nullptr;
 
+  const bool verbose = std::getenv("GE_VERBOSE") != nullptr;
+  double t_mark = now_ms();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double t = now_ms();
+    std::fprintf(stderr, "[ge] level n=%d %-18s %8.3f ms\n", n, what, t - t_mark);
+    t_mark = t;
+  };
   // ---- host: bin aggregates by size and lay out the slots -------------------------------------
   std::vector<int> by_size[33];
   std::vector<int> cta_aggs, grid_aggs;
@@ -314,6 +335,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     }
   }
 
+  lap("host layout");
   // ---- upload ------------------------------------------------------------------------------
   DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1)), d_vA(ctx, std::max(n, 1)), d_vtx(ctx, (size_t)ld), d_slot_of(ctx, std::max(n, 1)), d_agg_base(ctx, std::max(m, 1)), d_agg_of_slot(ctx, (size_t)ld), d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
   DevBuf<double> d_Dw, d_cA(ctx, (size_t)std::max(m, 1) * dim), d_rA(ctx, std::max(m, 1)), d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
@@ -332,11 +354,20 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
   d_cA.upload(ctx, coords_A, (size_t)m * dim);
   d_rA.upload(ctx, r_A, m);
-  d_init.upload(ctx, init, (size_t)n * dim);
+  if (init != nullptr) {
+    d_init.upload(ctx, init, (size_t)n * dim);
+  } else {
+    const int64_t count = (int64_t)n * dim;
+    const uint64_t seed64 = ((uint64_t)resolve_seed(0) << 32) | resolve_seed(0);
+    if (count > 0)
+      k_random_init<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_init.get(), count, seed64);
+    ctx->launches++;
+  }
   d_eb.zero(ctx->stream);
   d_ee.zero(ctx->stream);
   if (agg_begin > 0 || agg_end < m) d_out.zero(ctx->stream);  // rows of other ranks' aggregates
 
+  lap("upload");
   // ---- prep --------------------------------------------------------------------------------
   PrepArgs<T> pa;
   pa.I = d_I.get();
@@ -366,6 +397,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     ctx->launches++;
   }
 
+  lap("prep kernel");
   OnchipArgs<T> oa;
   oa.init_aos = d_init.get();
   oa.vtx = d_vtx.get();
@@ -475,8 +507,10 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     ctx->launches++;
   }
 
+  lap("solve kernels");
   d_out.download(ctx, coords_out, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  lap("download");
 }
 
 }  // namespace

@@ -245,3 +245,22 @@ def test_config3_config5_full_size(ctx, capi, graphs, name):
     else:                   # Delaunay tetrahedralisation of 4M points: ~62M entries
         As, Ps = graphs.coarsen(graphs.delaunay3d(4_000_000, seed=1), 0.125, min_coarse=64)
     _embed_properties(ctx, capi, As, Ps, 3)
+
+
+def test_unseeded_mode_draws_on_device(ctx, capi, graphs):
+    """seed = 0 is the reference's std::random_device mode: two runs differ, both are valid
+    layouts (finite, every member inside its parent ball)."""
+    As, Ps = _case(graphs, "rgg_big_aggs")
+    A, P = As[0], Ps[0]
+    m = P.shape[0]
+    rng = np.random.default_rng(2)
+    cA, rA = rng.normal(size=(m, 2)) * 5, rng.random(m) * 0.3 + 0.05
+    x1 = ctx.multilevel_forceatlas(A, P, cA, rA, 2, capi.multilevel_params(seed=0))
+    x2 = ctx.multilevel_forceatlas(A, P, cA, rA, 2, capi.multilevel_params(seed=0))
+    v_A = capi.vertex_to_aggregate(P)
+    for x in (x1, x2):
+        assert np.isfinite(x).all()
+        assert (np.linalg.norm(x - cA[v_A], axis=1) <= rA[v_A] * (1 + 1e-12)).all()
+    assert not np.array_equal(x1, x2)
+    e1, _ = ctx.embed(As, Ps, 2, seed=0, coarse_iterations=500)
+    assert np.isfinite(e1).all()
