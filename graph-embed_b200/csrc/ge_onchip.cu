@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
-    if (owner) {
-      for (int j0 = part; j0 < S; j0 += L * U) {
+    {  // every lane runs the pair loop (lanes without a vertex compute a discarded row), so the
+       // warp-wide clamp vote inside it is executed convergently
+      for (int j0 = part; j0 < ((a.debug_skip & 1) ? 0 : S); j0 += L * U) {
         T d[U][D], r2[U], s3[U], m0[U], m1[U], m2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -171,8 +172,10 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
             d[u][k] = x[k] - xj[k];
             r2[u] = fma(d[u][k], d[u][k], r2[u]);
           }
-          r2[u] = Real<T>::clamp_lo(r2[u], ph.eps2);
         }
+        // one warp-uniform clamp test for the U pairs; it also starts a basic block in which the
+        // U reciprocal-square-root chains below stay interleaved (ILP = U)
+        Real<T>::template clamp_lo_n<U>(r2, ph.eps2);
         Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2, s3);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -182,6 +185,8 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+    }
+    if (owner) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (eb + part + q * L < ee) {
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
     }
-    vertex_step<T, D, ML>(x, f, fprev, E, ci, ph);
+    if (!(a.debug_skip & 2)) vertex_step<T, D, ML>(x, f, fprev, E, ci, ph);
     if (a.forces_only) break;
     if (owner && part == 0) {
 #pragma unroll
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 512) k_onchip_cta(const OnchipArg
     const T* tmp = pc;
     pc = pn;
     pn = const_cast<T*>(tmp);
-    __syncthreads();
+    if (!(a.debug_skip & 4)) __syncthreads();
   }
 
   if (a.forces_only) {
@@ -371,8 +376,9 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
-    if (owner) {
-      for (int j0 = part; j0 < S; j0 += L * U) {
+    {  // every lane runs the pair loop (lanes without a vertex compute a discarded row), so the
+       // warp-wide clamp vote inside it is executed convergently
+      for (int j0 = part; j0 < ((a.debug_skip & 1) ? 0 : S); j0 += L * U) {
         T d[U][D], r2[U], s3[U], m0[U], m1[U], m2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -386,8 +392,10 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
             d[u][k] = x[k] - xj[k];
             r2[u] = fma(d[u][k], d[u][k], r2[u]);
           }
-          r2[u] = Real<T>::clamp_lo(r2[u], ph.eps2);
         }
+        // one warp-uniform clamp test for the U pairs; it also starts a basic block in which the
+        // U reciprocal-square-root chains below stay interleaved (ILP = U)
+        Real<T>::template clamp_lo_n<U>(r2, ph.eps2);
         Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2, s3);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -397,6 +405,8 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+    }
+    if (owner) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (eb + part + q * L < ee) {
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
     }
-    vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
+    if (!(a.debug_skip & 2)) vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
     if (owner) {  // the L lanes of the group share out the csize peer stores
       for (int rr = part; rr < csize; rr += L) {
         T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
@@ -546,16 +556,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_onchip_warp(const OnchipA
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
-    if (active) {
-      for (int j = base; j < base + s; ++j) {  // the self pair contributes exactly 0 (Q4)
-        T xj[D];
+    {
+      // U = 4 members per trip (all lanes, so that the clamp vote is convergent) (the self pair contributes exactly 0, Q4; lanes past the end of
+      // the aggregate re-read its first member with mass 0)
+      for (int j0 = base; j0 < base + s; j0 += 4) {
+        T d[4][D], r2[4], s3[4], m0[4], m1[4], m2[4];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xj[k] = pos_s[warp][cur][k][j];
-        pair_accumulate<T, D>(x, xj, ms_s[warp][0][j], ms_s[warp][NM > 1 ? 1 : 0][j],
-                              ms_s[warp][NM > 2 ? 2 : 0][j], a.ph.eps2, f);
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = j0 + u < base + s;
+          const int j = ok ? j0 + u : base;
+          r2[u] = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[u][k] = x[k] - pos_s[warp][cur][k][j];
+            r2[u] = fma(d[u][k], d[u][k], r2[u]);
+          }
+          m0[u] = ok ? ms_s[warp][0][j] : (T)0;
+          m1[u] = ok ? ms_s[warp][NM > 1 ? 1 : 0][j] : (T)0;
+          m2[u] = ok ? ms_s[warp][NM > 2 ? 2 : 0][j] : (T)0;
+        }
+        Real<T>::template clamp_lo_n<4>(r2, a.ph.eps2);
+        Real<T>::template inv_cube_mass_v<4>(r2, m0, m1, m2, s3);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) f[k] = fma(d[u][k], s3[u], f[k]);
+        }
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] *= ci_repel;
+    }
+    if (active) {
       for (int e = eb; e < ee; ++e) {
         const int j = a.e_idx[e] - slot0;
         const T w = (a.e_w != nullptr && a.ph.use_weights) ? a.e_w[e] : (T)1;
@@ -788,6 +819,7 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   a.forces_only = forces_only ? 1 : 0;
   a.normalize = p.normalize;
   a.ph = make_physics<T>(p);
+  if (const char* v = std::getenv("GE_ONCHIP_SKIP")) a.debug_skip = std::atoi(v);
   // Larger coarsest levels are spread over a thread-block cluster (measured crossover n ~ 40).
   int csize = 1;
   if (!forces_only) {

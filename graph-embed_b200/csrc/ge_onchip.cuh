@@ -29,6 +29,7 @@ struct OnchipArgs {
   double* out_aos = nullptr;         // [n][D] final coordinates (or forces when forces_only)
   int iters = 0;
   int forces_only = 0;
+  int debug_skip = 0;                // measurement only (GE_ONCHIP_SKIP): 1 = no pair loop, 2 = no epilogue, 4 = no barrier
   int normalize = 0;                 // flat epilogue of include/forceatlas.hpp:272-303
   Physics<T> ph;
 };

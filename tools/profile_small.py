@@ -49,6 +49,23 @@ elif mode == "k3sweep":
                 ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters, precision=prec))
                 ts.append(time.time() - t)
             print("n=%d nnz=%d cluster=%d L=%d: %.3f us/iter (overhead %.2f ms)" % (n, Ac.nnz, cs, L, 1e6 * (ts[1] - ts[0]) / 20000, 1e3 * ts[0]), flush=True)
+elif mode == "k3parts":
+    import time
+    for target, dim in ((42, 3), (34, 2), (91, 2)):
+        A = graphs.rgg(40 * target, 10.0, seed=1)
+        As, Ps = graphs.coarsen(A, 0.25, min_coarse=target)
+        Ac = As[-1]
+        n = Ac.shape[0]
+        x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
+        for skip in (0, 1, 2, 3):
+            os.environ["GE_ONCHIP_SKIP"] = str(skip)
+            ts = []
+            for iters in (1, 20001):
+                ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters))
+                t = time.time()
+                ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters))
+                ts.append(time.time() - t)
+            print("n=%d d=%d skip=%d (1=pairs 2=epilogue 4=barrier): %.3f us/iter" % (n, dim, skip, 1e6 * (ts[1] - ts[0]) / 20000), flush=True)
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     prec = capi.GE_F32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else capi.GE_F64
