@@ -716,10 +716,10 @@ const void* cluster_kernel(int L) {
 template <typename T>
 void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int dim, int csize) {
   const int per_cta = (n + csize - 1) / csize;
-  // measured (tools/profile_small.py k3sweep): with the vertices spread over several SMs the
-  // widest lane group that fits wins (n = 108: 8 CTAs x 32 lanes 1.5 us/iteration vs 3.3 us on one CTA)
+  // measured (tools/profile_small.py k3sweep): 8 lanes per vertex, as in the single-CTA kernel
+  // (n = 73: 8 CTAs x 8 lanes 1.3 us/iteration vs 2.2 us on one CTA; n = 157: 1.8 us)
   int L = 1;
-  while (L < 32 && per_cta * (L * 2) <= 512) L *= 2;
+  while (L < 8 && per_cta * (L * 2) <= 512) L *= 2;
   if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::atoi(v);
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
   GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");
@@ -823,7 +823,7 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   // Larger coarsest levels are spread over a thread-block cluster (measured crossover n ~ 40).
   int csize = 1;
   if (!forces_only) {
-    csize = n >= 80 ? 8 : n >= 40 ? 4 : 1;
+    csize = n >= 64 ? 8 : n >= 40 ? 4 : 1;
     if (const char* v = std::getenv("GE_CLUSTER")) csize = std::atoi(v);
     csize = std::max(1, std::min(csize, 8));
   }
