@@ -188,7 +188,10 @@ ge_status ge_flat_plan_bind_coords(ge_flat_plan* plan, void* dev_buf0, void* dev
 ge_status ge_flat_plan_upload_coords(ge_flat_plan* plan, const double* coords);   /* n x dim */
 ge_status ge_flat_plan_download_coords(ge_flat_plan* plan, double* coords);       /* n x dim */
 ge_status ge_flat_plan_download_forces(ge_flat_plan* plan, double* forces);       /* owned rows x dim */
-/* Device pointers of the current / next coordinate buffer. */
+/* Device pointers of the current / next coordinate buffer (SoA [dim][ld]).  Row order is the
+ * caller's for plans that own a row block of a multi-rank run; a plan that owns every row of a
+ * large graph may renumber the vertices internally (breadth-first, for gather locality) and
+ * restores the caller's order only in upload / download. */
 void* ge_flat_plan_cur_coords(ge_flat_plan* plan);
 void* ge_flat_plan_next_coords(ge_flat_plan* plan);
 /* Launch the kernels of one iteration for the owned rows (asynchronous on the context stream). */

@@ -183,3 +183,32 @@ def test_cluster_solve_matches_single_cta(ctx, capi, oracle, csize, dim, monkeyp
         monkeypatch.setenv("GE_CLUSTER", str(csize))
         xc = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k))
         assert np.array_equal(x1, xc), np.abs(x1 - xc).max()
+
+
+def test_internal_renumbering_is_transparent(ctx, capi, oracle, graphs, monkeypatch):
+    """Single-rank plans on large graphs renumber the vertices breadth-first for gather locality;
+    forces and positions come back in the caller's numbering and agree with the un-renumbered
+    plan (summation order inside a row changes, hence the tolerance) and with the oracle."""
+    A = graphs.rgg(70_000, 10.0, seed=3)
+    n = A.shape[0]
+    x0 = capi.reference_uniform(13, n * 3).reshape(n, 3)
+    p = capi.flat_params()
+    out = {}
+    for tag, env in (("bfs", None), ("plain", "1")):
+        if env:
+            monkeypatch.setenv("GE_NO_REORDER", env)
+        else:
+            monkeypatch.delenv("GE_NO_REORDER", raising=False)
+        plan = ctx.flat_plan(A, 3, p)
+        plan.upload(x0)
+        plan.iterate(2)
+        out[tag] = (plan.download(), plan.download_forces())
+        plan.close()
+    assert np.abs(out["bfs"][0] - out["plain"][0]).max() < 1e-11
+    scale = np.linalg.norm(out["plain"][1], axis=1).max()
+    assert np.abs(out["bfs"][1] - out["plain"][1]).max() < 1e-10 * scale
+    rows = np.random.default_rng(1).choice(n, 16, replace=False)
+    F = ctx.flat_forces(A, 3, x0, p, path=1)
+    for r in rows:
+        F_ref, S = oracle.flat_forces(A, 3, x0, rows=(int(r), int(r) + 1))
+        assert np.linalg.norm(F[r] - F_ref[r]) / S[r] < TOL_F64
