@@ -110,7 +110,7 @@ def galerkin(A, P_T):
     return canonical(P_T @ A @ P_T.T)
 
 
-def _matching_round(S, rng):
+def _matching_round(S, rng, max_merges=None):
     """One random-mate contraction round on the coarse graph S: vertices are split at random into
     heads and tails; every tail merges into the head neighbour with the best affinity
     w_ij / (k_i k_j) (several tails may pick the same head, so hubs grow stars, as the reference's
@@ -131,6 +131,9 @@ def _matching_round(S, rng):
     is_best = score == np.repeat(best, np.diff(np.r_[starts, rows.size]))
     sel = np.flatnonzero(is_best)
     tails, first = np.unique(rows[sel], return_index=True)
+    if max_merges is not None and tails.size > max_merges:   # stop exactly at the level's target size
+        keep = np.sort(rng.choice(tails.size, size=max_merges, replace=False))
+        tails, first = tails[keep], first[keep]
     label = np.arange(m)
     label[tails] = cols[sel[first]]
     uniq, new = np.unique(label, return_inverse=True)
@@ -139,15 +142,17 @@ def _matching_round(S, rng):
 
 def coarsen(A, coarsening_factor=0.25, min_coarse=64, max_levels=32, seed=0):
     """Hierarchy generator: returns (As, P_Ts) with As[l+1] = P_Ts[l] As[l] P_Ts[l]^T and
-    len(As) == len(P_Ts) + 1, each level reducing the vertex count to <= coarsening_factor
-    (a ratio M/N, like src/partitioner.cpp:1797) until <= min_coarse vertices remain."""
+    len(As) == len(P_Ts) + 1, each level reducing the vertex count to coarsening_factor x the
+    previous one (a ratio M/N, like src/partitioner.cpp:1797) but never below min_coarse, which
+    is the size of the coarsest level (the reference's hierarchies end at ~30-100 vertices)."""
     rng = np.random.default_rng(seed)
     As, P_Ts = [canonical(A)], []
     while As[-1].shape[0] > min_coarse and len(P_Ts) < max_levels:
         N = As[-1].shape[0]
         agg, M, S = np.arange(N), N, As[-1]
-        while M > coarsening_factor * N and M > min_coarse // 2:
-            res = _matching_round(S, rng)
+        target = max(int(np.floor(coarsening_factor * N)), min_coarse)
+        while M > target:
+            res = _matching_round(S, rng, max_merges=M - target)
             if res is None:
                 break
             new, M2 = res
