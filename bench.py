@@ -33,6 +33,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class stdout_to_stderr:
+    """The reference prints progress lines on std::cout (src/embed.cpp:583, 613); keep the
+    process's stdout for the one JSON line by pointing fd 1 at stderr while reference code runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -386,7 +405,12 @@ def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
         plan.close()
         ms = prof["attract_step_ms"] / prof["attract_step_launches"]
         b = algorithmic(n, nnz, dim, w)["step_bytes"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if w == 8 and n > 1_900_000 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("k_attract_step_f64_d3_n2m_bytes_per_launch")
         out[name] = {"kernel": "k_attract_step<%s,3>" % ("double" if w == 8 else "float"), "bound": "hbm",
+                     "traffic": traffic,
                      "unit": "GB/s", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                      "frac": b / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms,
                      "bytes_per_launch": b, "n": n, "nnz": nnz, "edge_visits_per_sec": nnz / (ms * 1e-3)}
@@ -425,7 +449,8 @@ def bench_embed(args, capi, ctx, graphs):
             threads = O.ref_lib("fast").ref_max_threads()
             best = None
             for nt in sorted({1, threads}):
-                _, secs = O.ref_embed(As, Ps, 2, seed=1, nthreads=nt, kind="fast")
+                with stdout_to_stderr():
+                    _, secs = O.ref_embed(As, Ps, 2, seed=1, nthreads=nt, kind="fast")
                 if best is None or secs < best[0]:
                     best = (secs, nt)
             out["cpu_reference_embed_wall_s"], out["cpu_reference_threads"] = best
