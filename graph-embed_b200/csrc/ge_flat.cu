@@ -91,12 +91,12 @@ struct VecLoad<float, 4> {
 // tail of one row block, sweeps whole row blocks, and starts the head of another.  Whole blocks
 // are written straight to F; shared blocks go to the CTA's two partial slots and are summed in a
 // fixed order by k_repulsion_fixup (deterministic, no atomics).
-template <typename T, int D, int IPT, int JU>
+template <typename T, int D, int IPT, int JU, int TJ>
 __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a) {
   constexpr int NM = Real<T>::kMassArrays;
   constexpr int NA = D + NM;
   constexpr int VEC = 16 / (int)sizeof(T);
-  constexpr uint32_t kStageBytes = NA * kTileJ * sizeof(T);
+  constexpr uint32_t kStageBytes = NA * TJ * sizeof(T);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tiles = reinterpret_cast<T*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kRepStages * kStageBytes);
@@ -145,15 +145,15 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
 
     auto issue = [&](int l) {  // l-th tile of this segment
       const unsigned s = (g + (unsigned)l) % kRepStages;
-      T* dst = tiles + (size_t)s * NA * kTileJ;
-      const int64_t j = (int64_t)bd.j0 + (int64_t)(t_begin + l) * kTileJ;
+      T* dst = tiles + (size_t)s * NA * TJ;
+      const int64_t j = (int64_t)bd.j0 + (int64_t)(t_begin + l) * TJ;
       mbar_expect_tx(&full[s], kStageBytes);
 #pragma unroll
       for (int k = 0; k < D; ++k)
-        tma_load_1d(dst + k * kTileJ, a.pos + (int64_t)k * a.ld + j, kTileJ * sizeof(T), &full[s]);
+        tma_load_1d(dst + k * TJ, a.pos + (int64_t)k * a.ld + j, TJ * sizeof(T), &full[s]);
 #pragma unroll
       for (int k = 0; k < NM; ++k)
-        tma_load_1d(dst + (D + k) * kTileJ, a.mass + (int64_t)k * a.ld + j, kTileJ * sizeof(T),
+        tma_load_1d(dst + (D + k) * TJ, a.mass + (int64_t)k * a.ld + j, TJ * sizeof(T),
                     &full[s]);
     };
     // The stages the prologue refills held tiles nt-3 / nt-2 of the previous segment, which every
@@ -168,15 +168,15 @@ __global__ void __launch_bounds__(kRepMaxThreads) k_repulsion(const RepArgs<T> a
       const unsigned gl = g + (unsigned)l;
       const unsigned s = gl % kRepStages;
       mbar_wait(&full[s], (gl / kRepStages) & 1u);
-      const T* st = tiles + (size_t)s * NA * kTileJ;
+      const T* st = tiles + (size_t)s * NA * TJ;
 
 #pragma unroll JU
-      for (int jj = 0; jj < kTileJ; jj += VEC) {
+      for (int jj = 0; jj < TJ; jj += VEC) {
         T xj[D][VEC], mj[3][VEC];
 #pragma unroll
-        for (int k = 0; k < D; ++k) VecLoad<T, VEC>::ld(st + k * kTileJ + jj, xj[k]);
+        for (int k = 0; k < D; ++k) VecLoad<T, VEC>::ld(st + k * TJ + jj, xj[k]);
 #pragma unroll
-        for (int k = 0; k < NM; ++k) VecLoad<T, VEC>::ld(st + (D + k) * kTileJ + jj, mj[k]);
+        for (int k = 0; k < NM; ++k) VecLoad<T, VEC>::ld(st + (D + k) * TJ + jj, mj[k]);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           // The IPT pairs of one column are independent: written stage by stage so that the
@@ -486,20 +486,25 @@ int env_int(const char* name, int dflt) {
 }
 
 template <typename T>
-size_t repulsion_smem(int dim) {
-  return (size_t)kRepStages * (dim + Real<T>::kMassArrays) * kTileJ * sizeof(T) +
+size_t repulsion_smem(int dim, int tj) {
+  return (size_t)kRepStages * (dim + Real<T>::kMassArrays) * tj * sizeof(T) +
          kRepStages * sizeof(uint64_t);
 }
 
-template <typename T, int D, int JU>
+template <typename T, int D, int JU, int TJ>
 const void* repulsion_kernel_d(int ipt) {
-  return ipt == 1 ? (const void*)k_repulsion<T, D, 1, JU>
-                  : ipt == 2 ? (const void*)k_repulsion<T, D, 2, JU> : (const void*)k_repulsion<T, D, 4, JU>;
+  return ipt == 1 ? (const void*)k_repulsion<T, D, 1, JU, TJ>
+                  : ipt == 2 ? (const void*)k_repulsion<T, D, 2, JU, TJ> : (const void*)k_repulsion<T, D, 4, JU, TJ>;
+}
+template <typename T, int TJ>
+const void* repulsion_kernel_t(int dim, int ipt, int ju) {
+  if (dim == 2) return ju == 1 ? repulsion_kernel_d<T, 2, 1, TJ>(ipt) : repulsion_kernel_d<T, 2, 2, TJ>(ipt);
+  return ju == 1 ? repulsion_kernel_d<T, 3, 1, TJ>(ipt) : repulsion_kernel_d<T, 3, 2, TJ>(ipt);
 }
 template <typename T>
-const void* repulsion_kernel(int dim, int ipt, int ju) {
-  if (dim == 2) return ju == 1 ? repulsion_kernel_d<T, 2, 1>(ipt) : repulsion_kernel_d<T, 2, 2>(ipt);
-  return ju == 1 ? repulsion_kernel_d<T, 3, 1>(ipt) : repulsion_kernel_d<T, 3, 2>(ipt);
+const void* repulsion_kernel(int dim, int ipt, int ju, int tj) {
+  return tj == kTileJSmall ? repulsion_kernel_t<T, kTileJSmall>(dim, ipt, ju)
+                           : repulsion_kernel_t<T, kTileJ>(dim, ipt, ju);
 }
 }  // namespace
 
@@ -510,14 +515,27 @@ RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowS
   // kernel is issue-bound): 512 threads, 2 rows per thread (4 for FP64 d = 3), the
   // column loop unrolled twice.  Small sweeps use narrower CTAs so that there are enough
   // (row block, tile) units to share out.
-  long long total_rows = 0;
-  for (const auto& sg : segments) total_rows += sg.row1 - sg.row0;
+  long long total_rows = 0, total_pairs = 0;
+  for (const auto& sg : segments) {
+    total_rows += sg.row1 - sg.row0;
+    total_pairs += (long long)(sg.row1 - sg.row0) * (sg.j1 - sg.j0);
+  }
   ipt_ = env_int("GE_REP_IPT", (sizeof(T) == 8 && dim == 3) ? 4 : 2);
   threads_ = env_int("GE_REP_THREADS", 512);
+  tile_ = kTileJ;
+  // Small sweeps (up to a few million pairs: large aggregates, graphs of 1-2 thousand vertices)
+  // are latency-bound per launch: fine-grained units (128 rows x 64 columns, one row per thread)
+  // put every SM to work instead of a handful of CTAs (measured n = 1000: 20 vs 30 us per
+  // iteration; from n = 4000 the wide configuration wins again).
+  if (total_pairs < 5000000LL && !std::getenv("GE_REP_THREADS")) {
+    tile_ = kTileJSmall;
+    threads_ = 128;
+    ipt_ = 1;
+  }
   while (threads_ > 128 && total_rows < (long long)ctx->sm_count * threads_ * ipt_) threads_ /= 2;
   ju_ = env_int("GE_REP_JU", 2);
-  const void* fn = repulsion_kernel<T>(dim_, ipt_, ju_);
-  const size_t smem = repulsion_smem<T>(dim_);
+  const void* fn = repulsion_kernel<T>(dim_, ipt_, ju_, tile_);
+  const size_t smem = repulsion_smem<T>(dim_, tile_);
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -527,7 +545,7 @@ RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowS
   std::vector<BlockDesc> blocks;
   long long units = 0;
   for (const auto& sg : segments) {
-    const int ntiles = (sg.j1 - sg.j0) / kTileJ;
+    const int ntiles = (sg.j1 - sg.j0) / tile_;
     for (int r = sg.row0; r < sg.row1; r += rows_per_block) {
       blocks.push_back(BlockDesc{r, std::min(sg.row1, r + rows_per_block), sg.j0, ntiles, units});
       units += ntiles;
@@ -541,8 +559,8 @@ RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowS
   partial_.alloc(ctx, (size_t)grid_ * 2 * dim_ * rows_per_block);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
   if (std::getenv("GE_VERBOSE"))
-    std::fprintf(stderr, "[ge] repulsion plan: threads=%d ipt=%d grid=%d (occ %d) blocks=%d units=%lld\n",
-                 threads_, ipt_, grid_, occ, nblocks_, total_units_);
+    std::fprintf(stderr, "[ge] repulsion plan: threads=%d ipt=%d tile=%d grid=%d (occ %d) blocks=%d units=%lld\n",
+                 threads_, ipt_, tile_, grid_, occ, nblocks_, total_units_);
 }
 
 template <typename T>
@@ -564,8 +582,8 @@ void RepulsionPlan<T>::launch(const T* pos, const T* mass, int64_t ld, T* F, int
   a.repel = repel;
   a.eps2 = eps2;
   void* args[] = {(void*)&a};
-  GE_CUDA(cudaLaunchKernel(repulsion_kernel<T>(dim_, ipt_, ju_), dim3(grid_), dim3(threads_), args,
-                           repulsion_smem<T>(dim_), ctx_->stream));
+  GE_CUDA(cudaLaunchKernel(repulsion_kernel<T>(dim_, ipt_, ju_, tile_), dim3(grid_), dim3(threads_), args,
+                           repulsion_smem<T>(dim_, tile_), ctx_->stream));
   ctx_->launches++;
   if (dim_ == 2) k_repulsion_fixup<T, 2><<<nblocks_, 256, 0, ctx_->stream>>>(a, grid_);
   else k_repulsion_fixup<T, 3><<<nblocks_, 256, 0, ctx_->stream>>>(a, grid_);

@@ -8,7 +8,8 @@
 
 namespace ge {
 
-constexpr int kTileJ = 256;      // column-tile entries
+constexpr int kTileJ = 256;      // column-tile entries (large sweeps); arrays are padded to this
+constexpr int kTileJSmall = 64;  // column-tile entries for small, latency-bound sweeps
 constexpr int kRepStages = 3;    // TMA pipeline depth
 constexpr int kRepMaxThreads = 512;
 
@@ -55,7 +56,7 @@ class RepulsionPlan {
 
  private:
   ge_context* ctx_;
-  int dim_, threads_ = 512, ipt_ = 2, ju_ = 1, grid_ = 0, nblocks_ = 0;
+  int dim_, threads_ = 512, ipt_ = 2, ju_ = 1, tile_ = kTileJ, grid_ = 0, nblocks_ = 0;
   long long total_units_ = 0;
   DevBuf<BlockDesc> blocks_;
   DevBuf<T> partial_;

@@ -212,3 +212,21 @@ def test_internal_renumbering_is_transparent(ctx, capi, oracle, graphs, monkeypa
     for r in rows:
         F_ref, S = oracle.flat_forces(A, 3, x0, rows=(int(r), int(r) + 1))
         assert np.linalg.norm(F[r] - F_ref[r]) / S[r] < TOL_F64
+
+
+def test_graph_replay_matches_eager_launches(ctx, capi, graphs, monkeypatch):
+    """Long flat solves on mid-size graphs replay a captured 2-iteration CUDA graph; the result is
+    bit-identical to launching every kernel eagerly (same kernels, same order)."""
+    A = graphs.rgg(3000, 10.0, seed=8)
+    n = A.shape[0]
+    x0 = capi.reference_uniform(2, n * 2).reshape(n, 2)
+    monkeypatch.setenv("GE_ONCHIP_MAX", "0")
+    for iters in (64, 101):
+        monkeypatch.delenv("GE_NO_GRAPH", raising=False)
+        l0 = ctx.launches
+        xg = ctx.flat_forceatlas(A, 2, x0, capi.flat_params(iterations=iters))
+        launched = ctx.launches - l0
+        monkeypatch.setenv("GE_NO_GRAPH", "1")
+        xe = ctx.flat_forceatlas(A, 2, x0, capi.flat_params(iterations=iters))
+        assert np.array_equal(xg, xe)
+        assert launched >= 3 * iters  # repulsion + fix-up + attraction/step per iteration are counted
