@@ -25,6 +25,81 @@ namespace ge {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+// ---------------------------------------------------------------------------------------------
+// staged host -> device copies
+// ---------------------------------------------------------------------------------------------
+struct Stager {
+  static constexpr size_t kChunk = size_t(4) << 20;
+  static constexpr int kThreads = 4, kSlotsPerThread = 2;
+  void* pinned[kThreads * kSlotsPerThread] = {};
+  cudaEvent_t ev[kThreads * kSlotsPerThread] = {};
+  bool ok = false;
+  Stager() {
+    ok = true;
+    for (int i = 0; i < kThreads * kSlotsPerThread; ++i) {
+      if (cudaHostAlloc(&pinned[i], kChunk, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+    }
+  }
+  ~Stager() {
+    for (int i = 0; i < kThreads * kSlotsPerThread; ++i) {
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      if (pinned[i]) cudaFreeHost(pinned[i]);
+    }
+  }
+};
+
+void host_to_device(ge_context* ctx, void* dst, const void* src, size_t bytes) {
+  bool direct = bytes < 4 * Stager::kChunk || std::getenv("GE_NO_STAGING") != nullptr;
+  if (!direct) {  // already page-locked (cudaHostAlloc / cudaHostRegister): the DMA engine reads it directly
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) direct = true;
+    cudaGetLastError();
+  }
+  if (direct) {
+    GE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return;
+  }
+  if (!ctx->stager) ctx->stager = new Stager();
+  Stager& st = *ctx->stager;
+  if (!st.ok) {
+    GE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return;
+  }
+  const size_t nchunks = (bytes + Stager::kChunk - 1) / Stager::kChunk;
+  std::atomic<int> failed(0);
+  auto worker = [&](int t) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) {
+      failed = 1;
+      return;
+    }
+    int turn = 0;
+    for (size_t c = t; c < nchunks; c += Stager::kThreads, ++turn) {
+      const int slot = t * Stager::kSlotsPerThread + (turn % Stager::kSlotsPerThread);
+      const size_t off = c * Stager::kChunk, sz = std::min(Stager::kChunk, bytes - off);
+      // the previous DMA out of this pinned buffer must have drained before it is refilled
+      if (cudaEventSynchronize(st.ev[slot]) != cudaSuccess) failed = 1;
+      std::memcpy(st.pinned[slot], (const char*)src + off, sz);
+      if (cudaMemcpyAsync((char*)dst + off, st.pinned[slot], sz, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+          cudaEventRecord(st.ev[slot], ctx->stream) != cudaSuccess)
+        failed = 1;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < Stager::kThreads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  if (failed) {
+    cudaGetLastError();
+    set_error("staged host->device copy failed");
+    throw Fail{GE_ERR_CUDA};
+  }
+}
+
 uint32_t resolve_seed(uint32_t seed) {
   if (seed != 0) return seed;
   std::random_device rd;  // what the reference does for every generator
@@ -519,6 +594,10 @@ ge_status ge_context_create(int device, void* cuda_stream, ge_context** out) {
 
 void ge_context_destroy(ge_context* ctx) {
   if (!ctx) return;
+  if (ctx->stager) {
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->stager;
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

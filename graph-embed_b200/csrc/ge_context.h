@@ -11,7 +11,12 @@
 
 #include "ge_common.cuh"
 
+namespace ge {
+struct Stager;  // pinned staging ring for large host->device copies (ge_capi.cu)
+}
+
 struct ge_context {
+  ge::Stager* stager = nullptr;
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -28,6 +33,11 @@ inline double now_ms() {
              std::chrono::steady_clock::now().time_since_epoch())
       .count();
 }
+
+// Host -> device copy on the context stream.  Large copies from pageable caller memory go through
+// a ring of pinned buffers filled by a few host threads (the driver's own pageable path is
+// single-threaded, ~12 GB/s on this box; the staged path overlaps four memcpy streams with the DMA).
+void host_to_device(ge_context* ctx, void* dst, const void* src, size_t bytes);
 
 // Owning device allocation from the stream-ordered memory pool of the context's device
 // (cudaMallocAsync / cudaFreeAsync on the context stream; the pool's release threshold is raised at
@@ -68,7 +78,7 @@ class DevBuf {
     if (n_) GE_CUDA(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s));
   }
   void upload(ge_context* ctx, const T* host, size_t n) {
-    if (n) GE_CUDA(cudaMemcpyAsync(p_, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) host_to_device(ctx, p_, host, n * sizeof(T));
     ctx->h2d_bytes += double(n * sizeof(T));
   }
   void download(ge_context* ctx, T* host, size_t n) const {
