@@ -76,18 +76,9 @@ struct Real<double> {
   }
   // s = cj * r2^(-3/2), with q = seed, e = 1 - r2 q^2:
   //   r2^(-3/2) = q^3 (1-e)^(-3/2) = q^3 (1 + 3/2 e + 15/8 e^2 + O(e^3)),   |e| <~ 4e-6
-  // so the truncation error is ~2.2 e^3 < 2e-16 relative.  6 FP64-pipe instructions.
-  __device__ __forceinline__ static double inv_cube_mass(double r2, double c, double c15,
-                                                         double c1875) {
-    const double q = rsqrt_seed(r2);
-    const double q2 = q * q;
-    const double e = fma(-r2, q2, 1.0);
-    const double q3 = q2 * q;
-    const double w = fma(e, fma(e, c1875, c15), c);
-    return q3 * w;
-  }
-  // The same for N independent pairs against one column, stage by stage (instruction-level
-  // parallelism across the pairs hides the FP64 pipe latency).
+  // so the truncation error is ~2.2 e^3 < 2e-16 relative.  6 FP64-pipe instructions per pair.
+  // N independent pairs against one column, stage by stage (instruction-level parallelism across
+  // the pairs hides the FP64 pipe latency).
   template <int N>
   __device__ __forceinline__ static void inv_cube_mass_n(const double (&r2)[N], double c, double c15,
                                                          double c1875, double (&s)[N]) {
@@ -160,10 +151,6 @@ struct Real<float> {
   __device__ __forceinline__ static void clamp_lo_n(float (&r2)[N], float lo) {
 #pragma unroll
     for (int t = 0; t < N; ++t) r2[t] = fmaxf(r2[t], lo);
-  }
-  __device__ __forceinline__ static float inv_cube_mass(float r2, float c, float, float) {
-    const float q = rsqrt_seed(r2);
-    return (q * q) * (q * c);
   }
   template <int N>
   __device__ __forceinline__ static void inv_cube_mass_n(const float (&r2)[N], float c, float, float,
@@ -296,24 +283,6 @@ __device__ __forceinline__ void vertex_step(T (&x)[D], T (&f)[D], T (&fprev)[D],
     x[k] = fma(f[k], speed, x[k]);
     fprev[k] = f[k];
   }
-}
-
-// One ordered pair of the repulsion sum (:154-165 / :397-408) accumulated into f; the common
-// factor (deg_i + 1) * repel is applied by the caller after the loop.
-template <typename T, int D>
-__device__ __forceinline__ void pair_accumulate(const T (&xi)[D], const T (&xj)[D], T m0, T m1,
-                                                T m2, T eps2, T (&f)[D]) {
-  T d[D];
-  T r2 = (T)0;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    d[k] = xi[k] - xj[k];
-    r2 = fma(d[k], d[k], r2);
-  }
-  r2 = Real<T>::clamp_lo(r2, eps2);
-  const T s3 = Real<T>::inv_cube_mass(r2, m0, m1, m2);
-#pragma unroll
-  for (int k = 0; k < D; ++k) f[k] = fma(d[k], s3, f[k]);
 }
 
 __host__ __device__ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }

@@ -132,7 +132,7 @@ void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
                       double* pairs_out, int agg_begin = 0, int agg_end = -1);
 
-// ---- ge_host.cpp -----------------------------------------------------------------------------
+// ---- ge_capi.cu (host-side level driver) -------------------------------------------------------
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                  const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);
 void reference_uniform(uint32_t seed, int64_t count, double* out);

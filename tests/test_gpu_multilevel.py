@@ -281,3 +281,15 @@ def test_staged_uploads_equal_direct_copies(ctx, capi, graphs, monkeypatch):
     monkeypatch.setenv("GE_NO_STAGING", "1")
     x2 = ctx.multilevel_forceatlas(As[0], Ps[0], cA, rA, 2, p)
     assert np.isfinite(x1).all() and np.array_equal(x1, x2)
+
+
+def test_embed_fp32_option(ctx, capi, graphs):
+    """precision = GE_F32 runs every kernel family in single precision: same exact prolongation
+    properties (the epilogue is evaluated in double), statistics close to the FP64 layout."""
+    As, Ps = graphs.coarsen(graphs.rgg(6000, 10.0, seed=4), 0.25, min_coarse=50)
+    x32, _ = ctx.embed(As, Ps, 2, seed=3, precision=capi.GE_F32)
+    x64, _ = ctx.embed(As, Ps, 2, seed=3, precision=capi.GE_F64)
+    assert np.isfinite(x32).all()
+    s32, s64 = layout_stats(As[0], x32), layout_stats(As[0], x64)
+    for key in s32:
+        assert abs(s32[key] - s64[key]) < 0.25 * abs(s64[key]), (key, s32, s64)
