@@ -288,7 +288,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     std::vector<int4> tasks;
     int threads = 32, size_max = 1;
   };
-  CtaClass cta_class[6];  // L = 1, 2, 4, 8, 16, 32
+  CtaClass cta_class[4];  // L = 1, 2, 4, 8
   for (int a : cta_aggs) {
     const int s = size_of(a);
     agg_base[a] = (int)cursor;
@@ -439,8 +439,8 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     launch_onchip_warp<T>(ctx, wa, (int)packs.size(), dim);
   }
   // ---- CTA tier ----------------------------------------------------------------------------
-  std::vector<DevBuf<int4>> d_cta_tasks(6);
-  for (int li = 0; li < 6; ++li) {
+  std::vector<DevBuf<int4>> d_cta_tasks(4);
+  for (int li = 0; li < 4; ++li) {
     CtaClass& cc = cta_class[li];
     if (cc.tasks.empty()) continue;
     d_cta_tasks[li].alloc(ctx, cc.tasks.size());

@@ -659,9 +659,7 @@ const void* cta_kernel_l(int L) {
     case 1: return (const void*)k_onchip_cta<T, D, ML, 1, BIG, GA>;
     case 2: return (const void*)k_onchip_cta<T, D, ML, 2, BIG, GA>;
     case 4: return (const void*)k_onchip_cta<T, D, ML, 4, BIG, GA>;
-    case 8: return (const void*)k_onchip_cta<T, D, ML, 8, BIG, GA>;
-    case 16: return (const void*)k_onchip_cta<T, D, ML, 16, BIG, GA>;
-    default: return (const void*)k_onchip_cta<T, D, ML, 32, BIG, GA>;
+    default: return (const void*)k_onchip_cta<T, D, ML, 8, BIG, GA>;
   }
 }
 template <typename T, int D, bool ML>
@@ -705,9 +703,7 @@ const void* cluster_kernel(int L) {
     case 1: return (const void*)k_onchip_cluster<T, D, 1, GA>;
     case 2: return (const void*)k_onchip_cluster<T, D, 2, GA>;
     case 4: return (const void*)k_onchip_cluster<T, D, 4, GA>;
-    case 8: return (const void*)k_onchip_cluster<T, D, 8, GA>;
-    case 16: return (const void*)k_onchip_cluster<T, D, 16, GA>;
-    default: return (const void*)k_onchip_cluster<T, D, 32, GA>;
+    default: return (const void*)k_onchip_cluster<T, D, 8, GA>;
   }
 }
 }  // namespace
@@ -720,7 +716,7 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   // (n = 73: 8 CTAs x 8 lanes 1.3 us/iteration vs 2.2 us on one CTA; n = 157: 1.8 us)
   int L = 1;
   while (L < 8 && per_cta * (L * 2) <= 512) L *= 2;
-  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::atoi(v);
+  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::min(8, std::max(1, std::atoi(v)));
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
   GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");
   const bool ga = a.ph.general_attraction != 0;

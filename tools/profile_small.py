@@ -37,7 +37,7 @@ elif mode == "k3sweep":
         Ac = As[-1]
         n = Ac.shape[0]
         x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
-        for cs, L in ((1, 8), (2, 8), (4, 8), (8, 8), (2, 16), (4, 16), (8, 16), (8, 32), (4, 4), (8, 4)):
+        for cs, L in ((1, 4), (1, 8), (2, 8), (4, 8), (8, 8), (4, 4), (8, 4)):
             if (n + cs - 1) // cs * L > (1024 if cs == 1 else 512):
                 continue
             os.environ["GE_ONCHIP_LANES"] = str(L)
