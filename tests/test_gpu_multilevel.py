@@ -293,3 +293,26 @@ def test_embed_fp32_option(ctx, capi, graphs):
     s32, s64 = layout_stats(As[0], x32), layout_stats(As[0], x64)
     for key in s32:
         assert abs(s32[key] - s64[key]) < 0.25 * abs(s64[key]), (key, s32, s64)
+
+
+@pytest.mark.parametrize("kw", [dict(use_weights=0), dict(linlog=1), dict(nohubs=1), dict(delta=0.5), dict(delta=0.0),
+                                dict(ks=0.3, ksmax=2.0, repel=2.0, attract=0.7, gravity=1.5, tolerate=0.8)])
+@pytest.mark.parametrize("cta_max", [512, 40])
+def test_multilevel_options(ctx, capi, oracle, graphs, kw, cta_max, monkeypatch):
+    """Non-default forceAtlasMultilevel arguments (include/forceatlas.hpp:320-331) on a weighted
+    Galerkin level with self-loops, through every tier: forces and 2-iteration positions."""
+    monkeypatch.setenv("GE_CTA_MAX", str(cta_max))
+    As, Ps = graphs.coarsen(graphs.rgg(6000, 10.0, seed=6), 0.1, min_coarse=10)
+    A, P = As[1], Ps[1]   # level 1: weighted edges + diagonal entries
+    n, m = A.shape[0], P.shape[0]
+    rng = np.random.default_rng(3)
+    cA, rA = rng.normal(size=(m, 2)), rng.random(m) * 0.3 + 0.05
+    okw = {"useWeights" if k == "use_weights" else k: v for k, v in kw.items()}
+    x = capi.reference_uniform(8, n * 2).reshape(n, 2)
+    _, F_ref, S = oracle.multilevel_run(A, P, cA, np.ones(m), 2, x, oracle.Params(iterations=1, **okw), forces_iter=0)
+    F = ctx.multilevel_forces(A, P, cA, x, 2, capi.multilevel_params(**kw))
+    assert force_error(F, F_ref, S).max() < TOL_F64
+    init = oracle.multilevel_init(P, 2, 5)
+    ref = oracle.multilevel_run(A, P, cA, rA, 2, init, oracle.Params(iterations=2, **okw))
+    got = ctx.multilevel_forceatlas(A, P, cA, rA, 2, capi.multilevel_params(iterations=2, **kw), init=init)
+    assert np.abs(got - ref).max() < 1e-10
