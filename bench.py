@@ -473,6 +473,12 @@ def bench_cpu_baseline(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version
+    # banner, the reference's progress lines) is pointed at stderr for the life of the process.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

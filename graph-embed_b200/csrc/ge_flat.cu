@@ -532,7 +532,11 @@ RepulsionPlan<T>::RepulsionPlan(ge_context* ctx, int dim, const std::vector<RowS
     threads_ = 128;
     ipt_ = 1;
   }
-  while (threads_ > 128 && total_rows < (long long)ctx->sm_count * threads_ * ipt_) threads_ /= 2;
+  // narrower CTAs only when there would otherwise be too few (row block, tile) units to share out
+  // (a 1/8 row block of a 500k-vertex graph still has 120k units: keep the wide shape)
+  while (threads_ > 128 &&
+         (total_pairs / ((long long)threads_ * ipt_ * tile_)) < 8LL * ctx->sm_count)
+    threads_ /= 2;
   ju_ = env_int("GE_REP_JU", 2);
   const void* fn = repulsion_kernel<T>(dim_, ipt_, ju_, tile_);
   const size_t smem = repulsion_smem<T>(dim_, tile_);
