@@ -427,6 +427,7 @@ struct EmbedRun {
   const ge_csr* Ps;
   ge_embed_options opt;
   ge_embed_stats st{};
+  double* final_out = nullptr;  // level 0 is written straight into the caller's buffer
 
   // embedMultilevel, src/embed.cpp:576-796.  Returns this level's coordinates; r_A / coords_A
   // receive the radii and (rescaled) coordinates of level+1, as the reference's out-params do.
@@ -479,11 +480,14 @@ struct EmbedRun {
     p.iterations = opt.level_iterations;  // :793
     p.precision = opt.precision;
     p.seed = opt.seed;
-    std::vector<double> coords((size_t)n * dim);
+    // the finest level (possibly hundreds of MB) goes straight into the caller's buffer
+    const bool direct = l == 0 && final_out != nullptr;
+    std::vector<double> coords(direct ? 0 : (size_t)n * dim);
     const double t1 = now_ms();
     double pairs = 0.0;
     multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(),
-                     init.empty() ? nullptr : init.data(), coords.data(), dim, p, false, &pairs);
+                     init.empty() ? nullptr : init.data(), direct ? final_out : coords.data(), dim, p,
+                     false, &pairs);
     st.levels_ms += now_ms() - t1;
     st.pair_interactions += pairs * p.iterations;
     st.edge_visits += double(A.nnz) * p.iterations;
@@ -691,8 +695,9 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     const double h0 = ctx->h2d_bytes, d0 = ctx->d2h_bytes;
     const double t0 = now_ms();
     std::vector<double> r_A, coords_A;
+    run.final_out = n_levels > 0 ? coords_out : nullptr;
     std::vector<double> coords = run.level(0, r_A, coords_A);
-    std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
+    if (!coords.empty()) std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
     if (r_A_out && !r_A.empty()) std::memcpy(r_A_out, r_A.data(), r_A.size() * sizeof(double));
     if (coords_A_out && !coords_A.empty())
       std::memcpy(coords_A_out, coords_A.data(), coords_A.size() * sizeof(double));
