@@ -168,8 +168,11 @@ def workload_config(args):
     return {"workload": "config4: flat single-level ForceAtlas, RGG n=%d avg degree 10, all-pairs "
                         "repulsion, dim=%d" % (args.n, args.dim),
             "n": args.n, "dim": args.dim, "avg_degree": 10,
-            "parallelism": "row-block x%d + coordinate all-gather per iteration" % args.gpus
-            if args.gpus > 1 else "single GPU",
+            "parallelism": ("single GPU" if args.gpus == 1 else
+                            "row-block x%d + coordinate all-gather per iteration" % args.gpus
+                            if getattr(args, "ordered", False) else
+                            "unordered pairs shared x%d (reduce-scatter of pair sums) + row-block x%d "
+                            "attraction/step + coordinate all-gather per iteration" % (args.gpus, args.gpus)),
             "l2": "flushed between timed steps (256 MiB device write outside the timed events)"}
 
 
@@ -208,7 +211,15 @@ def run_ours(args):
 
     # row blocks: ld is a multiple of 256, hence of every N in {1,2,4,8}
     r0, r1, R, probe_ld = sharding.row_block(n, world, rank)
-    plan = ctx.flat_plan(A, dim, params, rows=(r0, r1))
+    # N > 1: symmetric plan -- each rank evaluates 1/N of the unordered pairs over the full length,
+    # one reduce-scatter of the pair sums, then attraction + step on its row block, one all-gather
+    # of the new coordinates.  --ordered keeps the ordered row-block sweep (no reduce-scatter).
+    sym_ranks = world > 1 and not args.ordered
+    if sym_ranks:
+        plan = ctx.flat_plan(A, dim, params, symmetric=(rank, world))
+        assert plan.rows == (r0, r1)
+    else:
+        plan = ctx.flat_plan(A, dim, params, rows=(r0, r1))
     ld = plan.ld
     assert ld == probe_ld
     tdt = torch.float64
@@ -217,9 +228,18 @@ def run_ours(args):
     plan.upload(x0)
     ptr_to_buf = {bufs[0].data_ptr(): bufs[0], bufs[1].data_ptr(): bufs[1]}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sums = None
+    if sym_ranks:
+        sums = torch.zeros(dim * ld, dtype=tdt, device=dev)
+        plan.bind_pair_sums(sums.data_ptr())
 
     def one_step():
-        plan.launch_iteration()
+        if sym_ranks:
+            plan.launch_repulsion()
+            sharding.reduce_scatter_pair_sums(dist, sums.view(dim, ld), rank, R)
+            plan.launch_step()
+        else:
+            plan.launch_iteration()
         if world > 1:  # in-place: own slice sits at rank*R of the output
             sharding.allgather_coords(dist, ptr_to_buf[plan.next_ptr()].view(dim, ld), rank, R)
         plan.swap()
@@ -274,9 +294,12 @@ def run_ours(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_repulsion_f64_d%d_bytes_per_launch" % dim)
+            traffic = json.load(open(tpath)).get(
+                "%s_f64_d%d_bytes_per_launch" % ("k_repulsion_sym" if plan.symmetric else "k_repulsion", dim))
         rep_flops = alg["pairs"] * rows_frac * alg["flops_per_pair"]
-        roof = {"kernel": "k_repulsion<double,%d>" % dim, "bound": "fp64", "unit": "TFLOP/s",
+        roof = {"kernel": "%s<double,%d>%s" % ("k_repulsion_sym" if plan.symmetric else "k_repulsion", dim,
+                                                " (+ k_sym_reduce)" if plan.symmetric else ""),
+                "bound": "fp64", "unit": "TFLOP/s",
                 "achieved": rep_flops / (rep_ms * 1e-3) / 1e12, "peak": fp64_peak,
                 "peak_source": "measured live: ge_measure_fma_peak (independent DFMA chains, all SMs, CUDA events)",
                 "traffic": traffic, "ms_per_launch": rep_ms, "share_of_step": rep_ms / (rep_ms + step_ms),
@@ -296,7 +319,7 @@ def run_ours(args):
                "roofline": roof, "roofline_attraction": roof2}
 
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------
-    e2e = bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier)
+    e2e = bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier, one_step)
     if rank == 0:
         out["e2e"] = e2e
 
@@ -316,7 +339,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier):
+def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier, one_step):
     """Same metric through the public host-buffer API, host<->device copies inside the timed
     region.  N = 1: ge_flat_forceatlas (the forceAtlas drop-in: graph + coordinates in from pinned
     host memory, coordinates out), one call per step.  N > 1: the row-block plan API with the
@@ -345,13 +368,11 @@ def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, 
         t = time.time()
         for _ in range(steps):
             plan.upload(x)
-            plan.launch_iteration()
-            sharding.allgather_coords(dist, ptr_to_buf[plan.next_ptr()].view(dim, ld), rank, R)
-            plan.swap()
+            one_step()
             x = plan.download()
         barrier()
         dt = time.time() - t
-        note = "flat plan: upload coords, iterate own rows, all-gather, download coords per step"
+        note = "flat plan: upload coords, one iteration (pair sums, exchange, step, all-gather), download coords per step"
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -372,6 +393,7 @@ def bench_fp32(args, capi, ctx, A, x0, alg):
     plan.profile(True)
     plan.iterate(5)
     prof = plan.profile_get()
+    kname = "k_repulsion_sym<float,%d> (+ k_sym_reduce)" if plan.symmetric else "k_repulsion<float,%d>"
     plan.close()
     rep_ms = prof["repulsion_ms"] / prof["repulsion_launches"]
     step_ms = prof["attract_step_ms"] / prof["attract_step_launches"]
@@ -379,7 +401,7 @@ def bench_fp32(args, capi, ctx, A, x0, alg):
     ach = alg["pairs"] * alg["flops_per_pair"] / (rep_ms * 1e-3) / 1e12
     return {"dtype": "f32", "pair_interactions_per_sec": alg["pairs"] / ((rep_ms + step_ms) * 1e-3),
             "iters_per_sec": 1e3 / (rep_ms + step_ms),
-            "roofline": {"kernel": "k_repulsion<float,%d>" % dim, "bound": "fp32", "unit": "TFLOP/s",
+            "roofline": {"kernel": kname % dim, "bound": "fp32", "unit": "TFLOP/s",
                          "achieved": ach, "peak": peak, "frac": ach / peak, "ms_per_launch": rep_ms,
                          "peak_source": "measured live: ge_measure_fma_peak"}}
 
@@ -488,6 +510,8 @@ def main():
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--ref-n", type=int, default=30_000)
     ap.add_argument("--attr-n", type=int, default=2_000_000)
+    ap.add_argument("--ordered", action="store_true",
+                    help="N > 1: ordered row-block sweep instead of the symmetric pair shares")
     ap.add_argument("--no-embed", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-attraction", action="store_true")

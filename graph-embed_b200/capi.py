@@ -67,6 +67,9 @@ SYMBOLS = [
     "ge_flat_plan_download_forces", "ge_flat_plan_cur_coords", "ge_flat_plan_next_coords",
     "ge_flat_plan_launch_iteration", "ge_flat_plan_swap", "ge_flat_plan_iterate",
     "ge_flat_plan_sync", "ge_flat_plan_select_kernels", "ge_flat_plan_profile", "ge_flat_plan_profile_get",
+    "ge_flat_plan_create_symmetric", "ge_flat_plan_is_symmetric", "ge_flat_plan_pair_sums",
+    "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
+    "ge_flat_symmetric_share",
 ]
 
 _lib = None
@@ -86,6 +89,8 @@ def lib():
         L.ge_flat_plan_ld.restype = C.c_int64
         L.ge_flat_plan_cur_coords.restype = C.c_void_p
         L.ge_flat_plan_next_coords.restype = C.c_void_p
+        L.ge_flat_plan_pair_sums.restype = C.c_void_p
+        L.ge_flat_plan_is_symmetric.restype = C.c_int32
         L.ge_reference_uniform.argtypes = [C.c_uint32, C.c_int64, _pd]
         L.ge_context_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ge_context_bytes.restype = None
@@ -271,20 +276,43 @@ class Context:
                                           _ptr(x, _pd), int(dim), C.byref(params), _ptr(F, _pd)))
         return F
 
-    def flat_plan(self, A, dim, params, rows=None):
-        return FlatPlan(self, A, dim, params, rows)
+    def flat_plan(self, A, dim, params, rows=None, symmetric=None):
+        """rows=(r0, r1): ordered row-block plan; symmetric=(rank, world): that rank's plan of a
+        symmetric multi-rank solve (see ge_flat_plan_create_symmetric)."""
+        return FlatPlan(self, A, dim, params, rows, symmetric)
+
+
+def symmetric_share(ld, rank, world):
+    """ge_flat_symmetric_share -> [(row0, row1, tile_first, ntiles, tile_sym0)] (host only)."""
+    L = lib()
+    L.ge_flat_symmetric_share.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    nb = L.ge_flat_symmetric_share(int(ld), int(rank), int(world), 0, None)
+    if nb < 0:
+        raise ValueError("bad arguments")
+    buf = np.zeros(max(nb, 1) * 5, dtype=np.int32)
+    L.ge_flat_symmetric_share(int(ld), int(rank), int(world), nb, buf.ctypes.data_as(C.c_void_p))
+    return [tuple(int(v) for v in buf[5 * i:5 * i + 5]) for i in range(nb)]
 
 
 class FlatPlan:
     """ge_flat_plan: device-resident flat solver for rows [r0, r1) of A."""
 
-    def __init__(self, ctx, A, dim, params, rows=None):
+    def __init__(self, ctx, A, dim, params, rows=None, symmetric=None):
         self.ctx, self.n, self.dim = ctx, A.shape[0], dim
         self.rows = rows if rows is not None else (0, A.shape[0])
         a = CsrView(A)
         self.h = C.c_void_p()
-        _check(lib().ge_flat_plan_create(ctx.h, a.ref(), int(dim), C.byref(params),
-                                         int(self.rows[0]), int(self.rows[1]), C.byref(self.h)))
+        if symmetric is not None:
+            rank, world = symmetric
+            ld = ((max(self.n, 1) + 255) // 256) * 256
+            R = ld // world
+            self.rows = (min(self.n, rank * R), min(self.n, (rank + 1) * R))
+            _check(lib().ge_flat_plan_create_symmetric(ctx.h, a.ref(), int(dim), C.byref(params),
+                                                       int(rank), int(world), C.byref(self.h)))
+        else:
+            _check(lib().ge_flat_plan_create(ctx.h, a.ref(), int(dim), C.byref(params),
+                                             int(self.rows[0]), int(self.rows[1]), C.byref(self.h)))
+        self.symmetric = bool(lib().ge_flat_plan_is_symmetric(self.h))
         self.ld = int(lib().ge_flat_plan_ld(self.h))
         self.elem_size = int(lib().ge_flat_plan_elem_size(self.h))
 
@@ -324,6 +352,18 @@ class FlatPlan:
 
     def launch_iteration(self):
         _check(lib().ge_flat_plan_launch_iteration(self.h))
+
+    def launch_repulsion(self):
+        _check(lib().ge_flat_plan_launch_repulsion(self.h))
+
+    def launch_step(self):
+        _check(lib().ge_flat_plan_launch_step(self.h))
+
+    def pair_sums_ptr(self):
+        return lib().ge_flat_plan_pair_sums(self.h)
+
+    def bind_pair_sums(self, ptr):
+        _check(lib().ge_flat_plan_bind_pair_sums(self.h, C.c_void_p(ptr)))
 
     def swap(self):
         lib().ge_flat_plan_swap(self.h)

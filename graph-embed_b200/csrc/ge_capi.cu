@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ge_context.h"
+#include "ge_flat.cuh"
 
 namespace ge {
 
@@ -771,6 +772,49 @@ ge_status ge_flat_plan_create(ge_context* ctx, const ge_csr* A, int dim, const g
     plan->solver.reset(make_flat_solver(ctx, *A, dim, *p, row_begin, row_end));
     *out = plan.release();
   });
+}
+ge_status ge_flat_plan_create_symmetric(ge_context* ctx, const ge_csr* A, int dim, const ge_params* p,
+                                        int32_t rank, int32_t world, ge_flat_plan** out) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    GE_REQUIRE(p && out, "null argument");
+    GE_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world size");
+    const int64_t ld = round_up(std::max(A->rows, 1), 256 /* column tile */);
+    GE_REQUIRE(ld % world == 0, "world size does not divide the padded row count");
+    const int64_t R = ld / world;
+    const int rb = (int)std::min<int64_t>(A->rows, rank * R);
+    const int re = (int)std::min<int64_t>(A->rows, (rank + 1) * R);
+    std::unique_ptr<ge_flat_plan> plan(new ge_flat_plan);
+    plan->solver.reset(make_flat_solver(ctx, *A, dim, *p, rb, re, rank, world));
+    GE_REQUIRE(plan->solver->symmetric(), "symmetric plan refused (graph too small, scratch too "
+                                          "large, or GE_REP_SYM=0)");
+    *out = plan.release();
+  });
+}
+int32_t ge_flat_symmetric_share(int64_t ld, int32_t rank, int32_t world, int32_t capacity,
+                                int32_t* blocks) {
+  if (ld <= 0 || ld % 256 || world < 1 || rank < 0 || rank >= world) return -1;
+  std::vector<int> v;
+  sym_share(ld, rank, world, v);
+  const int nb = (int)v.size() / 5;
+  if (blocks)
+    for (int i = 0; i < std::min(nb, (int)capacity) * 5; ++i) blocks[i] = v[i];
+  return nb;
+}
+int32_t ge_flat_plan_is_symmetric(const ge_flat_plan* plan) { return plan->solver->symmetric() ? 1 : 0; }
+void* ge_flat_plan_pair_sums(ge_flat_plan* plan) { return plan->solver->pair_sums(); }
+ge_status ge_flat_plan_bind_pair_sums(ge_flat_plan* plan, void* dev_buf) {
+  return guarded([&] {
+    GE_REQUIRE(plan && dev_buf, "null argument");
+    plan->solver->bind_pair_sums(dev_buf);
+  });
+}
+ge_status ge_flat_plan_launch_repulsion(ge_flat_plan* plan) {
+  return guarded([&] { plan->solver->launch_repulsion(); });
+}
+ge_status ge_flat_plan_launch_step(ge_flat_plan* plan) {
+  return guarded([&] { plan->solver->launch_step(true); });
 }
 void ge_flat_plan_destroy(ge_flat_plan* plan) { delete plan; }
 int64_t ge_flat_plan_ld(const ge_flat_plan* plan) { return plan->solver->ld(); }

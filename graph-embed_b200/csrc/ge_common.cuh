@@ -98,6 +98,26 @@ struct Real<double> {
 #pragma unroll
     for (int t = 0; t < N; ++t) s[t] = q2[t] * w[t];
   }
+  // s = r2^(-3/2) without a mass factor (the symmetric sweep applies c_j on the row side and c_i
+  // on the column side): same series with the constants 1, 3/2, 15/8.
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_n(const double (&r2)[N], double (&s)[N]) {
+    double q[N], q2[N], e[N], w[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) e[t] = fma(-r2[t], q2[t], 1.0);
+#pragma unroll
+    for (int t = 0; t < N; ++t) q2[t] = q2[t] * q[t];
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], 1.875, 1.5);
+#pragma unroll
+    for (int t = 0; t < N; ++t) w[t] = fma(e[t], w[t], 1.0);
+#pragma unroll
+    for (int t = 0; t < N; ++t) s[t] = q2[t] * w[t];
+  }
   // N independent pairs against N different columns.
   template <int N>
   __device__ __forceinline__ static void inv_cube_mass_v(const double (&r2)[N], const double (&c)[N],
@@ -160,6 +180,14 @@ struct Real<float> {
     for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
 #pragma unroll
     for (int t = 0; t < N; ++t) s[t] = (q[t] * q[t]) * (q[t] * c);
+  }
+  template <int N>
+  __device__ __forceinline__ static void inv_cube_n(const float (&r2)[N], float (&s)[N]) {
+    float q[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = rsqrt_seed(r2[t]);
+#pragma unroll
+    for (int t = 0; t < N; ++t) s[t] = (q[t] * q[t]) * q[t];
   }
   template <int N>
   __device__ __forceinline__ static void inv_cube_mass_v(const float (&r2)[N], const float (&c)[N],

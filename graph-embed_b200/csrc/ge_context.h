@@ -107,7 +107,14 @@ class FlatSolver {
   virtual void download_forces(double* aos) = 0;  // owned rows x dim (forces_prev)
   virtual void* cur_coords() = 0;
   virtual void* next_coords() = 0;
-  virtual void launch_iteration(bool update) = 0;
+  virtual void launch_iteration(bool update) = 0;  // = launch_repulsion + launch_step
+  virtual void launch_repulsion() = 0;
+  virtual void launch_step(bool update) = 0;
+  // symmetric sweep (ge_flat_sym.cu): raw pair sums [dim][ld]; a multi-rank caller binds its own
+  // buffer and adds the ranks' sums between launch_repulsion and launch_step
+  virtual bool symmetric() const = 0;
+  virtual void bind_pair_sums(void* full) = 0;
+  virtual void* pair_sums() = 0;
   virtual void swap() = 0;
   virtual void normalize() = 0;  // include/forceatlas.hpp:272-303 (single rank)
   virtual void select_kernels(int mask) = 0;
@@ -115,8 +122,9 @@ class FlatSolver {
   virtual void profile_get(double* rep_ms, int64_t* rep_n, double* step_ms, int64_t* step_n) = 0;
   ge_context* ctx = nullptr;
 };
+// part / parts: rank of a symmetric multi-rank solve (rows must be that rank's row block)
 FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
-                             int row_begin, int row_end);
+                             int row_begin, int row_end, int part = 0, int parts = 1);
 
 // ---- ge_onchip.cu ----------------------------------------------------------------------------
 // Small flat solve entirely inside one CTA (coarsest level: n ~ 30-100, 100 000 iterations).

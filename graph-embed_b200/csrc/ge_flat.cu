@@ -18,71 +18,9 @@
 #include <vector>
 
 #include "ge_flat.cuh"
+#include "ge_tma.cuh"
 
 namespace ge {
-
-// ---- mbarrier / TMA bulk-copy primitives ------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
-               "r"(bytes)
-               : "memory");
-}
-// Waits for the phase with the given parity.  try_wait suspends the thread in hardware for a
-// bounded time per call; the poll count is bounded too, so a bulk copy that never lands (a bug)
-// traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_addr(bar);
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-// 1-D TMA: global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_addr(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-      : "memory");
-}
-
-template <typename T, int VEC>
-struct VecLoad;
-template <>
-struct VecLoad<double, 2> {
-  __device__ __forceinline__ static void ld(const double* p, double (&v)[2]) {
-    const double2 t = *reinterpret_cast<const double2*>(p);
-    v[0] = t.x;
-    v[1] = t.y;
-  }
-};
-template <>
-struct VecLoad<float, 4> {
-  __device__ __forceinline__ static void ld(const float* p, float (&v)[4]) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x;
-    v[1] = t.y;
-    v[2] = t.z;
-    v[3] = t.w;
-  }
-};
 
 // K1a.  Each thread owns IPT rows (positions and force accumulators in registers); the CTA walks
 // column tiles.  Thread 0 is the TMA producer; everybody consumes through broadcast shared-memory
@@ -328,11 +266,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
   for (int k = 0; k < D; ++k) {
     x[k] = a.pos_cur[(int64_t)k * a.ld + i];
     f[k] = (T)0;
-    frep[k] = finisher ? a.Frep[(int64_t)k * a.ldf + r] : (T)0;
+    frep[k] = finisher ? a.Frep[(int64_t)k * (a.ldr ? a.ldr : a.ldf) + r] : (T)0;
     fprev[k] = (finisher && a.update) ? a.Fprev[(int64_t)k * a.ldf + r] : (T)0;
     E[k] = (ML && finisher && a.Eext != nullptr) ? a.Eext[(int64_t)k * a.ldf + r] : (T)0;
   }
   const T ci = a.mass[i];
+  if (a.frep_scale != (T)0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) frep[k] *= ci * a.frep_scale;
+  }
   const bool weighted = a.W != nullptr && a.ph.use_weights;
   // EU entries per lane and trip: all index loads, then all gathers, are in flight together
   // (memory-level parallelism; the kernel is latency-bound long before it is issue-bound)
@@ -649,8 +591,9 @@ namespace {
 template <typename T>
 class FlatSolverT final : public FlatSolver {
  public:
-  FlatSolverT(ge_context* c, const ge_csr& A, int dim, const ge_params& p, int rb, int re)
-      : n_(A.rows), dim_(dim), rb_(rb), re_(re) {
+  FlatSolverT(ge_context* c, const ge_csr& A, int dim, const ge_params& p, int rb, int re,
+              int part, int parts)
+      : n_(A.rows), dim_(dim), rb_(rb), re_(re), parts_(parts) {
     ctx = c;
     ph_ = make_physics<T>(p);
     ld_ = round_up(std::max(n_, 1), kTileJ);
@@ -761,7 +704,31 @@ class FlatSolverT final : public FlatSolver {
     Fprev_.zero(ctx->stream);
     stage_.alloc(ctx, (size_t)std::max(n_, 1) * dim_);
 
-    rep_.reset(new RepulsionPlan<T>(ctx, dim_, {RowSegment{rb_, re_, 0, (int)ld_}}));
+    // Whole-graph plans on large graphs evaluate every unordered pair once (ge_flat_sym.cu); the
+    // column-side scratch grows with n^2 / 2048, so very large graphs (and row-block plans, whose
+    // pairs are not closed under transposition) keep the ordered sweep.
+    {
+      const char* e = std::getenv("GE_REP_SYM");
+      // parts > 1: this plan is rank `part` of a symmetric multi-rank solve -- it evaluates its
+      // share of the unordered pairs over the FULL length and the ranks add their sums
+      // (reduce-scatter) before the step; row-block plans (parts == 1, rows != all) cannot.
+      bool want = (e ? std::atoi(e) != 0 : true) && (parts_ > 1 || (rb_ == 0 && re_ == n_)) &&
+                  n_ >= env_int("GE_SYM_MIN_ROWS", 32768);
+      if (want) {
+        size_t free_b = 0, total_b = 0;
+        GE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        want = RepulsionSymPlan<T>::scratch_bytes(dim_, ld_, parts_) < 0.5 * double(free_b);
+      }
+      GE_REQUIRE(want || parts_ == 1, "symmetric multi-rank plan refused (graph too small / too "
+                                      "large for the column scratch, or GE_REP_SYM=0)");
+      if (want) {
+        sym_.reset(new RepulsionSymPlan<T>(ctx, dim_, ld_, part, parts_));
+        S_.alloc(ctx, (size_t)dim_ * ld_);
+        sums_ = S_.get();
+      } else {
+        rep_.reset(new RepulsionPlan<T>(ctx, dim_, {RowSegment{rb_, re_, 0, (int)ld_}}));
+      }
+    }
     for (auto& e : ev_) GE_CUDA(cudaEventCreate(&e));
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -825,12 +792,33 @@ class FlatSolverT final : public FlatSolver {
     stepped_ = false;
   }
 
+  bool symmetric() const override { return sym_ != nullptr; }
+  void bind_pair_sums(void* full) override {
+    GE_REQUIRE(sym_ != nullptr, "not a symmetric plan");
+    sums_ = (T*)full;
+  }
+  void* pair_sums() override { return sums_; }
   void launch_iteration(bool update) override {
-    if (nrows_ == 0) return;
+    GE_REQUIRE(!(sym_ && parts_ > 1),
+               "multi-rank symmetric plan: call launch_repulsion, add the ranks' sums, then launch_step");
+    launch_repulsion();
+    launch_step(update);
+  }
+  void launch_repulsion() override {
+    if (nrows_ == 0 && !sym_) return;
     if (prof_) GE_CUDA(cudaEventRecord(ev_[0], ctx->stream));
-    if (kernel_mask_ & 1)
-      rep_->launch(buf_[cur_], mass_.get(), ld_, Frep_.get(), ldf_, rb_, ph_.repel, ph_.eps2);
-    if (prof_) GE_CUDA(cudaEventRecord(ev_[1], ctx->stream));
+    if (kernel_mask_ & 1) {
+      if (sym_) sym_->launch(buf_[cur_], mass_.get(), sums_, ph_.eps2);
+      else rep_->launch(buf_[cur_], mass_.get(), ld_, Frep_.get(), ldf_, rb_, ph_.repel, ph_.eps2);
+    }
+    if (prof_) {  // read back after the step, so that the step queues behind the sweep as usual
+      GE_CUDA(cudaEventRecord(ev_[1], ctx->stream));
+      rep_pending_ = true;
+    }
+  }
+  void launch_step(bool update) override {
+    if (nrows_ == 0) return;
+    if (prof_) GE_CUDA(cudaEventRecord(ev_[2], ctx->stream));
     StepArgs<T> sa;
     sa.e_begin = rowptr_.get();
     sa.e_end = rowptr_.get() + 1;
@@ -848,6 +836,11 @@ class FlatSolverT final : public FlatSolver {
       sa.aos_next = aos_[cur_ ^ 1].get();
     }
     sa.Frep = Frep_.get();
+    if (sym_) {  // raw pair sums over the full length; the step kernel applies c_i * repel
+      sa.Frep = sums_ + rb_;
+      sa.ldr = ld_;
+      sa.frep_scale = ph_.repel;
+    }
     sa.Fprev = Fprev_.get();
     sa.mass = mass_.get();
     sa.Eext = nullptr;
@@ -862,15 +855,18 @@ class FlatSolverT final : public FlatSolver {
       stepped_ = update;
     }
     if (prof_) {
-      GE_CUDA(cudaEventRecord(ev_[2], ctx->stream));
-      GE_CUDA(cudaEventSynchronize(ev_[2]));
-      float t_rep = 0, t_step = 0;
-      GE_CUDA(cudaEventElapsedTime(&t_rep, ev_[0], ev_[1]));
-      GE_CUDA(cudaEventElapsedTime(&t_step, ev_[1], ev_[2]));
-      rep_ms_ += t_rep;
+      GE_CUDA(cudaEventRecord(ev_[3], ctx->stream));
+      GE_CUDA(cudaEventSynchronize(ev_[3]));
+      float t_step = 0, t_rep = 0;
+      GE_CUDA(cudaEventElapsedTime(&t_step, ev_[2], ev_[3]));
       step_ms_ += t_step;
-      rep_n_++;
       step_n_++;
+      if (rep_pending_) {
+        GE_CUDA(cudaEventElapsedTime(&t_rep, ev_[0], ev_[1]));
+        rep_ms_ += t_rep;
+        rep_n_++;
+        rep_pending_ = false;
+      }
     }
   }
 
@@ -896,7 +892,8 @@ class FlatSolverT final : public FlatSolver {
   }
 
  private:
-  int n_, dim_, rb_, re_, nrows_ = 0;
+  int n_, dim_, rb_, re_, parts_ = 1, nrows_ = 0;
+  T* sums_ = nullptr;  // [dim][ld] raw pair sums of the symmetric sweep (own S_ or caller-bound)
   int64_t ld_ = 0, ldf_ = 0;
   Physics<T> ph_;
   double avg_deg_ = 0;
@@ -905,6 +902,8 @@ class FlatSolverT final : public FlatSolver {
   bool aos_valid_ = false, stepped_ = false;
   DevBuf<int> rowptr_, J_, perm_;
   std::unique_ptr<RepulsionPlan<T>> rep_;
+  std::unique_ptr<RepulsionSymPlan<T>> sym_;
+  DevBuf<T> S_;
   DevBuf<double> stage_;
   T* buf_[2] = {nullptr, nullptr};
   int cur_ = 0;
@@ -912,18 +911,21 @@ class FlatSolverT final : public FlatSolver {
   int kernel_mask_ = 3;
   double rep_ms_ = 0, step_ms_ = 0;
   int64_t rep_n_ = 0, step_n_ = 0;
-  cudaEvent_t ev_[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool rep_pending_ = false;
 };
 
 }  // namespace
 
 FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
-                             int row_begin, int row_end) {
+                             int row_begin, int row_end, int part, int parts) {
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
   GE_REQUIRE(A.rows == A.cols, "A must be square");
   GE_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A.rows, "bad row block");
-  if (p.precision == GE_F32) return new FlatSolverT<float>(ctx, A, dim, p, row_begin, row_end);
-  return new FlatSolverT<double>(ctx, A, dim, p, row_begin, row_end);
+  GE_REQUIRE(parts >= 1 && part >= 0 && part < parts, "bad rank / world size");
+  if (p.precision == GE_F32)
+    return new FlatSolverT<float>(ctx, A, dim, p, row_begin, row_end, part, parts);
+  return new FlatSolverT<double>(ctx, A, dim, p, row_begin, row_end, part, parts);
 }
 
 }  // namespace ge

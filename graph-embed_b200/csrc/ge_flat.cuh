@@ -62,6 +62,61 @@ class RepulsionPlan {
   DevBuf<T> partial_;
 };
 
+// ---- symmetric all-pairs sweep (ge_flat_sym.cu) ------------------------------------------------
+// The pair term is antisymmetric ((xi-xj) ci cj repel / dis^3, include/forceatlas.hpp:154-165), so
+// every unordered pair is evaluated once and applied to both endpoints.  The sweep covers the
+// upper triangle of (row block, column tile) units: tiles inside the row block's own rows are
+// evaluated in full (row side only), tiles to the right of it feed the row AND the column.
+struct SymBlockDesc {
+  int row0, row1;     // rows of the block
+  int t_first;        // first column tile (global tile index) of this plan's units in the block
+  int ntiles;         // number of units (consecutive tiles)
+  int tile_sym0;      // tiles >= tile_sym0 lie to the right of the block: symmetric
+  int col_t0, ncols;  // column slab of this block in `colpartial`: tiles from col_t0, ncols columns
+  long long unit0;    // exclusive prefix sum of ntiles
+  long long col_off;  // element offset of the slab, laid out [D][ncols]
+};
+
+template <typename T>
+struct RepSymArgs {
+  const T* pos;      // [D][ld]
+  const T* mass;     // [ld]  c = deg + 1 (0 on padding)
+  T* S;              // [D][ld] raw sums: sum_j c_j (xi-xj)/dis^3 over every pair this plan owns
+  T* partial;        // [grid][2][D][rows_per_block] row sums of blocks shared between CTAs
+  T* colpartial;     // column-side sums, one slab per block (written exactly once per launch)
+  const SymBlockDesc* blocks;
+  int64_t ld;
+  long long total_units;
+  int nblocks, rows_per_block;
+  int gb0;           // global index (row0 / rows_per_block) of blocks[0]
+  T eps2;
+};
+
+// Launch plan of the symmetric sweep over rows/columns [0, ld): share `part` of `parts` equal
+// contiguous cuts of the triangular unit list (parts > 1: every rank produces partial sums over
+// the full length, which the ranks add with a reduce-scatter).
+template <typename T>
+class RepulsionSymPlan {
+ public:
+  RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int part, int parts);
+  // bytes of column-side scratch the plan would need (worst share)
+  static double scratch_bytes(int dim, int64_t ld, int parts);
+  // S[k][i] = sum over this plan's pairs; multiply by c_i * repel to obtain the force
+  void launch(const T* pos, const T* mass, T* S, T eps2);
+  long long pairs() const { return pairs_; }  // ordered pairs covered by one launch
+
+ private:
+  ge_context* ctx_;
+  int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0, gb0_ = 0;
+  int64_t ld_ = 0;
+  long long total_units_ = 0, pairs_ = 0;
+  DevBuf<SymBlockDesc> blocks_;
+  DevBuf<T> partial_, colpartial_;
+};
+
+// The (row0, row1, tile_first, ntiles, tile_sym0) quintuples of share `part` of `parts` (host).
+void sym_share(int64_t ld, int part, int parts, std::vector<int>& out);
+
 template <typename T>
 struct StepArgs {
   const int* e_begin;  // per owned row: first / one-past-last entry in J, W
@@ -75,7 +130,9 @@ struct StepArgs {
   // L2 sector instead of one per dimension.  nullptr: gather from the SoA arrays.
   const T* aos_cur = nullptr;  // [ld][DP]
   T* aos_next = nullptr;       // [ld][DP]
-  const T* Frep;       // [D][ldf] (owned rows)
+  const T* Frep;       // [D][ldr] (owned rows)
+  int64_t ldr = 0;     // leading dimension of Frep (0: ldf)
+  T frep_scale = 0;    // != 0: Frep holds raw pair sums, force = Frep * c_i * frep_scale
   T* Fprev;            // [D][ldf]
   const T* mass;       // [ld]
   const T* Eext;       // [D][ldf] multilevel external-pull numerators, or nullptr

@@ -3,8 +3,14 @@
 Rank r owns rows [r*R, min((r+1)*R, n)) with R = ld / world, where ld is the leading dimension of
 the SoA coordinate buffers (n padded to the 256-entry column tile, hence divisible by 1, 2, 4, 8).
 Every rank keeps the full coordinates; after each iteration the ranks exchange their freshly
-written slices with one in-place all-gather per coordinate dimension (the only collective of the
-path: the reference's global swing / traction sums are dead code)."""
+written slices with one in-place all-gather per coordinate dimension (the reference's global
+swing / traction sums are dead code, SURVEY.md section 0.3, so there is no all-reduce).
+
+Symmetric plans (large graphs): the repulsion term is antisymmetric, so every unordered pair is
+evaluated once, on one rank -- the upper triangle of (row block, column tile) units is cut into
+equal shares (`pair_share`), each rank accumulates its pairs' contributions over the full length,
+and one in-place reduce-scatter per dimension (`reduce_scatter_pair_sums`) hands every rank the
+complete sums of its own rows before attraction + step."""
 
 
 def padded_ld(n, tile=256):
@@ -25,6 +31,43 @@ def allgather_coords(dist, nxt, rank, R):
     In-place all-gather per dimension (NCCL: sendbuff == recvbuff + rank * count)."""
     for k in range(nxt.shape[0]):
         dist.all_gather_into_tensor(nxt[k], nxt[k, rank * R:(rank + 1) * R])
+
+
+def pair_share(ld, world, rank, rows_per_block=1024, tile=256):
+    """The share of the symmetric all-pairs sweep that rank `rank` evaluates (mirror of
+    sym_layout in csrc/ge_flat_sym.cu).  The upper triangle is the list of (row block, column
+    tile) units -- block g covers rows [g*rows_per_block, ...) and the tiles from its own first row
+    to the end -- cut into `world` equal contiguous shares.  Returns
+    [(row0, row1, tile_first, ntiles, tile_sym0)]: tiles below tile_sym0 lie inside the block's own
+    rows (every ordered pair evaluated, row side only); tiles from tile_sym0 on are evaluated once
+    and applied to both the rows and the columns."""
+    ntile = ld // tile
+    nblk = (ld + rows_per_block - 1) // rows_per_block
+    per_block = [ntile - (g * rows_per_block) // tile for g in range(nblk)]
+    total = sum(per_block)
+    U0, U1 = total * rank // world, total * (rank + 1) // world
+    out, prefix = [], 0
+    for g in range(nblk):
+        tf = (g * rows_per_block) // tile
+        b0, b1 = prefix, prefix + per_block[g]
+        prefix = b1
+        lo, hi = max(b0, U0), min(b1, U1)
+        if lo >= hi:
+            continue
+        row0, row1 = g * rows_per_block, min(ld, (g + 1) * rows_per_block)
+        out.append((row0, row1, tf + (lo - b0), hi - lo, (row1 + tile - 1) // tile))
+    return out
+
+
+def reduce_scatter_pair_sums(dist, sums, rank, R):
+    """sums: [dim, ld] tensor of this rank's raw pair sums over the full length.  Afterwards its
+    columns [rank*R, (rank+1)*R) hold the sum over all ranks (in place; NCCL: recvbuff == sendbuff
+    + rank * count).  gloo has no reduce-scatter: the CPU tests use an all-reduce instead."""
+    for k in range(sums.shape[0]):
+        if dist.get_backend() == "gloo":
+            dist.all_reduce(sums[k])
+        else:
+            dist.reduce_scatter_tensor(sums[k, rank * R:(rank + 1) * R], sums[k])
 
 
 def aggregate_blocks(A, P_T, world):

@@ -180,6 +180,35 @@ void ge_reference_uniform(uint32_t seed, int64_t count, double* out);
 ge_status ge_flat_plan_create(ge_context* ctx, const ge_csr* A, int dim, const ge_params* p,
                               int32_t row_begin, int32_t row_end, ge_flat_plan** out);
 void ge_flat_plan_destroy(ge_flat_plan* plan);
+/* Rank `rank` of a `world`-rank SYMMETRIC solve of the same loop (include/forceatlas.hpp:151-167
+ * adds an exactly antisymmetric term for (i,j) and (j,i), so each unordered pair is evaluated
+ * once, on one rank).  The rank owns the row block [rank*ld/world, (rank+1)*ld/world) (clipped to
+ * n) for attraction + step, and an equal share of the unordered pairs for repulsion, whose sums it
+ * accumulates over the FULL length [dim][ld].  Per iteration:
+ *     ge_flat_plan_launch_repulsion            (pair sums of this rank's share)
+ *     reduce-scatter (sum) of the pair sums    (caller: NCCL, per dimension, in place; the buffer
+ *                                               is ge_flat_plan_pair_sums or the caller's own,
+ *                                               bound with ge_flat_plan_bind_pair_sums)
+ *     ge_flat_plan_launch_step                 (attraction, gravity, step for the owned rows)
+ *     all-gather of the next coordinates, ge_flat_plan_swap   (as for row-block plans)
+ * world == 1 is the plan ge_flat_plan_create makes for all rows.  GE_ERR_INVALID if the graph is
+ * too small for the symmetric sweep (n < 32768) or its scratch would not fit. */
+ge_status ge_flat_plan_create_symmetric(ge_context* ctx, const ge_csr* A, int dim, const ge_params* p,
+                                        int32_t rank, int32_t world, ge_flat_plan** out);
+/* Host-only: the units of rank `rank`'s share of the symmetric sweep over a padded length ld (a
+ * multiple of 256) as quintuples (row0, row1, first column tile, tile count, first symmetric
+ * tile); returns the number of quintuples (at most `capacity` are written), -1 on bad arguments. */
+int32_t ge_flat_symmetric_share(int64_t ld, int32_t rank, int32_t world, int32_t capacity,
+                                int32_t* blocks);
+/* 1 if the plan evaluates unordered pairs (ge_flat_plan_create chooses this for whole-graph plans
+ * on large graphs), 0 for the ordered row-block sweep. */
+int32_t ge_flat_plan_is_symmetric(const ge_flat_plan* plan);
+/* Symmetric plans: the [dim][ld] device buffer of raw pair sums (force = sum * c_i * repel). */
+void* ge_flat_plan_pair_sums(ge_flat_plan* plan);
+ge_status ge_flat_plan_bind_pair_sums(ge_flat_plan* plan, void* dev_buf);
+/* The two halves of ge_flat_plan_launch_iteration. */
+ge_status ge_flat_plan_launch_repulsion(ge_flat_plan* plan);
+ge_status ge_flat_plan_launch_step(ge_flat_plan* plan);
 /* Leading dimension (elements) of the SoA coordinate buffers and element size in bytes. */
 int64_t ge_flat_plan_ld(const ge_flat_plan* plan);
 int32_t ge_flat_plan_elem_size(const ge_flat_plan* plan);

@@ -85,3 +85,12 @@ def test_invalid_arguments(capi):
                          P_T_c=__import__("scipy.sparse").sparse.identity(4, format="csr"),
                          coords_Ac=np.zeros((4, 2)), r_Ac=np.ones(4))
     assert e.value.status == capi.GE_ERR_INVALID
+
+
+def test_symmetric_share_matches_python_mirror(capi):
+    """The C++ cut of the triangular unit list (csrc/ge_flat_sym.cu) == sharding.pair_share."""
+    from graph_embed_b200 import sharding
+    for ld in (256, 1024, 2304, 500_224):
+        for world in (1, 2, 4, 8):
+            for rank in range(world):
+                assert capi.symmetric_share(ld, rank, world) == sharding.pair_share(ld, world, rank)

@@ -130,3 +130,88 @@ def test_level_output_exchange_is_exact(tmp_path):
     mp.spawn(_sum_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     got, full = np.load(out)
     assert np.array_equal(got, full)
+
+
+def _pair_sums_share(x, c, share, tile=256):
+    """numpy restatement of one rank's share of the symmetric sweep: raw sums
+    S_i += c_j (xi-xj)/dis^3 (rows), S_j -= c_i (xi-xj)/dis^3 (columns of symmetric tiles)."""
+    ld, dim = x.shape
+    S = np.zeros_like(x)
+    for row0, row1, tf, nt, tsym in share:
+        for t in range(tf, tf + nt):
+            j0, j1 = t * tile, (t + 1) * tile
+            d = x[row0:row1, None, :] - x[None, j0:j1, :]
+            r2 = np.maximum((d * d).sum(-1), 1e-10)
+            s = r2 ** -1.5
+            S[row0:row1] += (d * (s * c[None, j0:j1])[..., None]).sum(1)
+            if t >= tsym:
+                S[j0:j1] -= (d * (s * c[row0:row1, None])[..., None]).sum(0)
+    return S
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_pair_shares_cover_every_unordered_pair_once(world):
+    """Summed over the ranks, the shares reproduce the ordered all-pairs sum of
+    include/forceatlas.hpp:151-167 (before the c_i * repel factor)."""
+    from graph_embed_b200 import sharding
+    rng = np.random.default_rng(1)
+    n, ld, dim = 2300, 2304, 2
+    x = np.zeros((ld, dim))
+    x[:n] = rng.uniform(-1, 1, (n, dim))
+    c = np.zeros(ld)
+    c[:n] = rng.integers(1, 9, n)
+    d = x[:, None, :] - x[None, :, :]
+    s = np.maximum((d * d).sum(-1), 1e-10) ** -1.5
+    full = (d * (s * c[None, :])[..., None]).sum(1)
+    shares = [sharding.pair_share(ld, world, r) for r in range(world)]
+    units = sorted((row0, t) for sh in shares for row0, _, tf, nt, _ in sh for t in range(tf, tf + nt))
+    assert len(units) == len(set(units))                      # no unit evaluated twice
+    assert len(units) == sum(ld // 256 - r0 // 256 for r0 in range(0, ld, 1024))
+    got = sum(_pair_sums_share(x, c, sh) for sh in shares)
+    assert np.abs(got[:n] - full[:n]).max() < 1e-9 * np.abs(full[:n]).max()
+    counts = [sum(nt for *_, nt, _ in sh) for sh in shares]
+    assert max(counts) - min(counts) <= 1                     # equal shares
+
+
+def _sym_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest  # noqa: F401
+    from graph_embed_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(2)
+    n, ld, dim = 2000, 2048, 3
+    x = np.zeros((ld, dim))
+    x[:n] = rng.uniform(-1, 1, (n, dim))
+    c = np.zeros(ld)
+    c[:n] = rng.integers(1, 9, n)
+    S = _pair_sums_share(x, c, sharding.pair_share(ld, world, rank))
+    sums = torch.from_numpy(np.ascontiguousarray(S.T))       # [dim, ld] like the device buffer
+    R = ld // world
+    sharding.reduce_scatter_pair_sums(dist, sums, rank, R)
+    own = sums[:, rank * R:(rank + 1) * R].clone()
+    gathered = [torch.zeros_like(own) for _ in range(world)]
+    dist.all_gather(gathered, own)
+    if rank == 0:
+        np.save(out, torch.cat(gathered, dim=1).numpy().T)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_symmetric_pair_sums(tmp_path):
+    """Two ranks, each with half of the unordered pairs: after the exchange every rank's own
+    rows hold the complete sums."""
+    out = str(tmp_path / "sums.npy")
+    mp.spawn(_sym_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    rng = np.random.default_rng(2)
+    n, ld, dim = 2000, 2048, 3
+    x = np.zeros((ld, dim))
+    x[:n] = rng.uniform(-1, 1, (n, dim))
+    c = np.zeros(ld)
+    c[:n] = rng.integers(1, 9, n)
+    d = x[:, None, :] - x[None, :, :]
+    s = np.maximum((d * d).sum(-1), 1e-10) ** -1.5
+    full = (d * (s * c[None, :])[..., None]).sum(1)
+    got = np.load(out)
+    assert np.abs(got[:n] - full[:n]).max() < 1e-9 * np.abs(full[:n]).max()
