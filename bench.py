@@ -306,7 +306,7 @@ def run_ours(args):
                 "pairs_per_launch": alg["pairs"] * rows_frac, "flops_per_pair": alg["flops_per_pair"]}
         roof["frac"] = roof["achieved"] / roof["peak"]
         step_bytes = alg["step_bytes"] * rows_frac
-        roof2 = {"kernel": "k_attract_step<double,%d>" % dim, "bound": "hbm", "unit": "GB/s",
+        roof2 = {"kernel": "k_attract_step_staged<double,%d>" % dim, "bound": "hbm", "unit": "GB/s",
                  "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "peak_source": hbm_src,
                  "traffic": None, "ms_per_launch": step_ms, "bytes_per_launch": step_bytes}
         roof2["frac"] = roof2["achieved"] / roof2["peak"]
@@ -412,10 +412,10 @@ def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
     n = args.attr_n
     t = time.time()
     A = graphs.rgg(n, 10.0, seed=11)
-    n, nnz, dim = A.shape[0], A.nnz, 3
+    n, nnz = A.shape[0], A.nnz
     log("[bench] attraction graph n=%d nnz=%d (%.1fs)" % (n, nnz, time.time() - t))
     out = {}
-    for prec, w, name in ((capi.GE_F64, 8, "f64"), (capi.GE_F32, 4, "f32")):
+    for prec, w, name, dim in ((capi.GE_F64, 8, "f64", 3), (capi.GE_F32, 4, "f32", 3), (capi.GE_F64, 8, "f64_d2", 2)):
         plan = ctx.flat_plan(A, dim, capi.flat_params(precision=prec))
         plan.upload(capi.reference_uniform(5, n * dim).reshape(n, dim))
         plan.select_kernels(2)  # attraction + step only: 4e12 ordered pairs per repulsion pass here
@@ -429,9 +429,9 @@ def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
         b = algorithmic(n, nnz, dim, w)["step_bytes"]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if w == 8 and n > 1_900_000 and os.path.exists(tpath):
+        if w == 8 and dim == 3 and n > 1_900_000 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("k_attract_step_f64_d3_n2m_bytes_per_launch")
-        out[name] = {"kernel": "k_attract_step<%s,3>" % ("double" if w == 8 else "float"), "bound": "hbm",
+        out[name] = {"kernel": "k_attract_step_staged<%s,%d>" % ("double" if w == 8 else "float", dim), "bound": "hbm",
                      "traffic": traffic,
                      "unit": "GB/s", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                      "frac": b / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms,

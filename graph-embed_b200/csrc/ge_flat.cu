@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <type_traits>
 #include <vector>
 
 #include "ge_flat.cuh"
@@ -335,6 +336,199 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
   }
 }
 
+// K1b+c, staged variant for contiguous CSR rows (the flat solver).  The chain of dependent loads
+// per row -- row pointer -> column index / weight -> neighbour coordinates -- is what bounds
+// k_attract_step (ncu: long-scoreboard stalls on the index and weight loads).  Here a persistent CTA
+// walks chunks of 256/G rows; thread 0 streams each chunk's slice of the index and weight arrays
+// into shared memory with 1-D TMA bulk copies ONE CHUNK AHEAD (two stages, mbarrier completion),
+// and the chunk bounds / row pointers are fetched one and two chunks ahead, so that while a chunk
+// is processed the only exposed latency is the coordinate gather itself.  A chunk with more than
+// kStepCap entries (very long rows) reads its indices from global memory as before.
+constexpr int kStepCap = 2560;  // staged entries per chunk and stage (multiple of 4: 16-byte copies)
+
+template <typename T, int D, int G, bool GA, int CAP, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArgs<T> a, const int nchunks) {
+  constexpr int kStepCap = CAP;
+  constexpr int RPC = 256 / G;
+  constexpr int EU = G <= 2 ? 4 : 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* Ws = reinterpret_cast<T*>(smem_raw);
+  int* Js = reinterpret_cast<int*>(smem_raw + 2 * kStepCap * sizeof(T));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * kStepCap * (sizeof(T) + sizeof(int)));
+  const int tid = threadIdx.x;
+  const int lane = tid % G, rl = tid / G;
+  const bool weighted = a.W != nullptr && a.ph.use_weights;
+  const int* __restrict__ rowptr = a.e_begin;  // contiguous CSR: e_end == e_begin + 1
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int c = blockIdx.x;
+  if (c >= nchunks) return;
+  const int stride = gridDim.x;
+
+  auto bounds = [&](int cc, int& b0, int& b1) {
+    const int r0 = cc * RPC;
+    b0 = rowptr[r0];
+    b1 = rowptr[min(r0 + RPC, a.nrows)];
+  };
+  auto row_range = [&](int cc, int& e0, int& e1) {
+    const int r = cc * RPC + rl;
+    const bool ok = r < a.nrows;
+    e0 = ok ? rowptr[r] : 0;
+    e1 = ok ? rowptr[r + 1] : 0;
+  };
+  auto staged_count = [](int b0, int b1) { return ((b1 - (b0 & ~3)) + 3) & ~3; };
+  auto issue = [&](int stage, int b0, int b1) {  // thread 0
+    const int base = b0 & ~3;
+    const int cnt = staged_count(b0, b1);
+    if (cnt <= 0 || cnt > kStepCap) return;
+    mbar_expect_tx(&full[stage], (uint32_t)cnt * (uint32_t)(sizeof(int) + (weighted ? sizeof(T) : 0)));
+    tma_load_1d(Js + stage * kStepCap, a.J + base, (uint32_t)cnt * sizeof(int), &full[stage]);
+    if (weighted) tma_load_1d(Ws + stage * kStepCap, a.W + base, (uint32_t)cnt * sizeof(T), &full[stage]);
+  };
+
+  int b0, b1, nb0 = 0, nb1 = 0, e0, e1;
+  bounds(c, b0, b1);
+  if (c + stride < nchunks) bounds(c + stride, nb0, nb1);
+  row_range(c, e0, e1);
+  if (tid == 0) issue(0, b0, b1);
+  unsigned phases = 0u;  // bit s: parity of the next completion of stage s
+  const T* posk[D];
+#pragma unroll
+  for (int kk = 0; kk < D; ++kk) posk[kk] = a.pos_cur + (int64_t)kk * a.ld;
+
+  for (unsigned k = 0;; ++k) {
+    const int stage = (int)(k & 1u);
+    const int cn = c + stride, cnn = c + 2 * stride;
+    const bool has_next = cn < nchunks;
+    // one chunk ahead: its copies; two ahead: its bounds; the next chunk's row pointers
+    if (tid == 0 && has_next) issue(stage ^ 1, nb0, nb1);
+    int nnb0 = 0, nnb1 = 0, ne0 = 0, ne1 = 0;
+    if (cnn < nchunks) bounds(cnn, nnb0, nnb1);
+    if (has_next) row_range(cn, ne0, ne1);
+
+    const int r = c * RPC + rl;
+    const bool active = r < a.nrows;
+    const int i = a.row0 + (active ? r : 0);
+    const bool finisher = active && lane == 0;
+    T x[D], f[D], frep[D], fprev[D];
+    const int64_t ldr = a.ldr ? a.ldr : a.ldf;
+#pragma unroll
+    for (int kk = 0; kk < D; ++kk) {
+      x[kk] = a.pos_cur[(int64_t)kk * a.ld + i];
+      f[kk] = (T)0;
+      frep[kk] = finisher ? a.Frep[(int64_t)kk * ldr + r] : (T)0;
+      fprev[kk] = (finisher && a.update) ? a.Fprev[(int64_t)kk * a.ldf + r] : (T)0;
+    }
+    const T ci = a.mass[i];
+
+    const int base = b0 & ~3;
+    const int cnt = staged_count(b0, b1);
+    const bool staged = cnt > 0 && cnt <= kStepCap;
+    if (staged) {
+      mbar_wait(&full[stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+    }
+    // The gather layout (interleaved copy or SoA) and the presence of weights are compile-time
+    // inside the walk: predicating both variants costs ~2x the issue slots of this loop.
+    auto walk = [&](auto aos_c, auto wt_c, const int* __restrict__ Jp, const T* __restrict__ Wp) {
+      constexpr bool AOS = decltype(aos_c)::value;
+      constexpr bool WT = decltype(wt_c)::value;
+      for (int e = e0 + lane; e < e1; e += EU * G) {
+        int jn[EU];
+        T wn[EU];  // 0 on the slots past the end of the row: their term vanishes
+        bool on[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const int eu = e + u * G;
+          on[u] = eu < e1;
+          jn[u] = on[u] ? Jp[eu] : i;
+          if (WT) wn[u] = on[u] ? Wp[eu] : (T)0;
+          else wn[u] = on[u] ? (T)1 : (T)0;
+        }
+        T dn[EU][D];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          if (AOS) {
+            Gather<T, D>::ld(a.aos_cur, jn[u], dn[u]);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk) dn[u][kk] = posk[kk][jn[u]];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          T r2 = (T)0;
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) {
+            dn[u][kk] -= x[kk];
+            if (GA) r2 = fma(dn[u][kk], dn[u][kk], r2);
+          }
+          T g;
+          if (GA) g = on[u] ? attraction_factor<T, true>(r2, WT ? wn[u] : (T)1, ci, a.ph) : (T)0;
+          else g = a.ph.attract * wn[u];
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) f[kk] = fma(dn[u][kk], g, f[kk]);
+        }
+      }
+    };
+    using std::false_type;
+    using std::true_type;
+    if (staged) {
+      const int* Jp = Js + stage * kStepCap - base;
+      const T* Wp = Ws + stage * kStepCap - base;
+      if (a.aos_cur != nullptr) {
+        if (weighted) walk(true_type{}, true_type{}, Jp, Wp);
+        else walk(true_type{}, false_type{}, Jp, Wp);
+      } else {
+        if (weighted) walk(false_type{}, true_type{}, Jp, Wp);
+        else walk(false_type{}, false_type{}, Jp, Wp);
+      }
+    } else {  // long rows: indices and weights straight from global memory
+      if (a.aos_cur != nullptr) {
+        if (weighted) walk(true_type{}, true_type{}, a.J, a.W);
+        else walk(true_type{}, false_type{}, a.J, a.W);
+      } else {
+        if (weighted) walk(false_type{}, true_type{}, a.J, a.W);
+        else walk(false_type{}, false_type{}, a.J, a.W);
+      }
+    }
+
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+#pragma unroll
+      for (int kk = 0; kk < D; ++kk) f[kk] += __shfl_xor_sync(0xffffffffu, f[kk], off, G);
+    }
+    if (finisher) {
+      if (a.frep_scale != (T)0) {
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) frep[kk] *= ci * a.frep_scale;
+      }
+      const T E[D] = {};
+#pragma unroll
+      for (int kk = 0; kk < D; ++kk) f[kk] += frep[kk];
+      vertex_step<T, D, false>(x, f, fprev, E, ci, a.ph);
+#pragma unroll
+      for (int kk = 0; kk < D; ++kk) {
+        a.Fprev[(int64_t)kk * a.ldf + r] = fprev[kk];
+        if (a.update) a.pos_next[(int64_t)kk * a.ld + i] = x[kk];
+      }
+      if (a.update && a.aos_next != nullptr) {
+        constexpr int DP = Gather<T, D>::DP;
+#pragma unroll
+        for (int kk = 0; kk < DP; ++kk) a.aos_next[(int64_t)i * DP + kk] = kk < D ? x[kk] : (T)0;
+      }
+    }
+    if (!has_next) break;
+    __syncthreads();  // everyone has left this chunk's stage: the copy issued next trip may refill it
+    c = cn;
+    b0 = nb0, b1 = nb1, nb0 = nnb0, nb1 = nnb1, e0 = ne0, e1 = ne1;
+  }
+}
+
 // include/forceatlas.hpp:127-140: c_i = 1 + sum of row weights (or row length).  Also emits the
 // two scaled copies the FP64 pair kernel consumes (1.5 c, 1.875 c).  One thread per row.
 template <typename T>
@@ -560,6 +754,53 @@ void launch_step_ga(ge_context* ctx, const StepArgs<T>& a, int group) {
 }
 }  // namespace
 
+namespace {
+template <typename T, int D, int G, bool GA, int CAP, int MINB>
+void launch_staged_c(ge_context* ctx, const StepArgs<T>& a) {
+  const size_t smem = 2 * CAP * (sizeof(T) + sizeof(int)) + 2 * sizeof(uint64_t);
+  auto fn = k_attract_step_staged<T, D, G, GA, CAP, MINB>;
+  static int occ = 0;  // per instantiation
+  if (occ == 0) {
+    GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, smem));
+    GE_REQUIRE(occ > 0, "staged attraction kernel does not fit on an SM");
+  }
+  const int rpc = 256 / G;
+  const int nchunks = (a.nrows + rpc - 1) / rpc;
+  const int grid = std::min(nchunks, ctx->sm_count * occ);
+  fn<<<grid, 256, smem, ctx->stream>>>(a, nchunks);
+}
+template <typename T, int D, int G, bool GA>
+void launch_staged_g(ge_context* ctx, const StepArgs<T>& a) {
+  static const int cap = env_int("GE_STEP_CAP", kStepCap);
+  if (cap <= 2048) launch_staged_c<T, D, G, GA, 2048, 4>(ctx, a);
+  else launch_staged_c<T, D, G, GA, kStepCap, 3>(ctx, a);
+}
+template <typename T, int D, bool GA>
+void launch_staged_d(ge_context* ctx, const StepArgs<T>& a, int group) {
+  // (a 3072-entry / 3-CTA shape of the one-lane variant spills at 85 registers: 47 % vs 58 %)
+  if (group <= 1) launch_staged_c<T, D, 1, GA, 4096, 2>(ctx, a);
+  else if (group <= 2) launch_staged_g<T, D, 2, GA>(ctx, a);
+  else if (group <= 4) launch_staged_g<T, D, 4, GA>(ctx, a);
+  else launch_staged_g<T, D, 8, GA>(ctx, a);
+}
+}  // namespace
+
+// Contiguous CSR rows (a.e_end == a.e_begin + 1), J / W padded by >= 4 entries, flat physics.
+template <typename T>
+void launch_attract_step_staged(ge_context* ctx, const StepArgs<T>& a, int dim, int group) {
+  if (a.nrows == 0) return;
+  if (dim == 2) {
+    if (a.ph.general_attraction) launch_staged_d<T, 2, true>(ctx, a, group);
+    else launch_staged_d<T, 2, false>(ctx, a, group);
+  } else {
+    if (a.ph.general_attraction) launch_staged_d<T, 3, true>(ctx, a, group);
+    else launch_staged_d<T, 3, false>(ctx, a, group);
+  }
+  GE_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 template <typename T>
 void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int group, bool ml) {
   if (a.nrows == 0) return;
@@ -678,14 +919,20 @@ class FlatSolverT final : public FlatSolver {
     for (int r = 0; r <= nrows_; ++r) rowptr[r] = I[rb_ + r] - e0;
     rowptr_.alloc(ctx, nrows_ + 1);
     rowptr_.upload(ctx, rowptr.data(), nrows_ + 1);
-    J_.alloc(ctx, std::max(lnnz, 1));
+    J_.alloc(ctx, lnnz + 8);  // + padding: the staged kernel copies 16-byte-aligned slices
+    GE_CUDA(cudaMemsetAsync(J_.get() + lnnz, 0, 8 * sizeof(int), ctx->stream));
     J_.upload(ctx, J + e0, lnnz);
     std::vector<T> w;
     if (weighted) {
-      w.resize(lnnz);
-      for (int e = 0; e < lnnz; ++e) w[e] = (T)Dw[e0 + e];
-      W_.alloc(ctx, std::max(lnnz, 1));
-      W_.upload(ctx, w.data(), lnnz);
+      W_.alloc(ctx, lnnz + 8);
+      GE_CUDA(cudaMemsetAsync(W_.get() + lnnz, 0, 8 * sizeof(T), ctx->stream));
+      if (std::is_same<T, double>::value) {  // no conversion: straight from the caller's array
+        W_.upload(ctx, reinterpret_cast<const T*>(Dw + e0), lnnz);
+      } else {
+        w.resize(lnnz);
+        for (int e = 0; e < lnnz; ++e) w[e] = (T)Dw[e0 + e];
+        W_.upload(ctx, w.data(), lnnz);
+      }
     }
     GE_CUDA(cudaStreamSynchronize(ctx->stream));  // the renumbered host arrays die with this scope
     avg_deg_ = nrows_ > 0 ? double(lnnz) / nrows_ : 0.0;
@@ -717,7 +964,8 @@ class FlatSolverT final : public FlatSolver {
       if (want) {
         size_t free_b = 0, total_b = 0;
         GE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        want = RepulsionSymPlan<T>::scratch_bytes(dim_, ld_, parts_) < 0.5 * double(free_b);
+        const double need = RepulsionSymPlan<T>::scratch_bytes(dim_, ld_, parts_);
+        want = need < 0.5 * double(free_b) && need < 1e9 * env_int("GE_SYM_MAX_SCRATCH_GB", 16);
       }
       GE_REQUIRE(want || parts_ == 1, "symmetric multi-rank plan refused (graph too small / too "
                                       "large for the column scratch, or GE_REP_SYM=0)");
@@ -826,7 +1074,7 @@ class FlatSolverT final : public FlatSolver {
     sa.W = W_.size() ? W_.get() : nullptr;
     sa.pos_cur = buf_[cur_];
     sa.pos_next = buf_[cur_ ^ 1];
-    if (use_gather_copy_ && perm_.size() == 0) {
+    if (use_gather_copy_ && (perm_.size() == 0 || gather_copy_reordered_)) {
       // (with the breadth-first renumbering the SoA gathers are already local and the copy only
       // costs its own write traffic: 0.158 ms without vs 0.182 ms with, n = 2M)
       // The copy of the current buffer is exact when this plan wrote every row of it in the
@@ -851,7 +1099,15 @@ class FlatSolverT final : public FlatSolver {
     sa.update = update ? 1 : 0;
     sa.ph = ph_;
     if (kernel_mask_ & 2) {
-      launch_attract_step<T>(ctx, sa, dim_, env_int("GE_STEP_GROUP", group_for_degree(avg_deg_)), false);
+      // one lane per row while a 256-row chunk fits the staging buffer (fewest instructions per
+      // row: measured 58-63 % of the HBM peak against 57-61 % with two lanes), else 2-8 lanes
+      const int group = env_int("GE_STEP_GROUP", avg_deg_ * 256 <= 0.8 * 4096 ? 1 : group_for_degree(avg_deg_));
+      // staged (TMA) variant: groups up to 8 lanes; chunks of 256/G rows must mostly fit kStepCap
+      if (staged_step_ && group <= 8 &&
+          avg_deg_ * (256 / std::max(group, 1)) <= 0.8 * (group <= 1 ? 4096 : kStepCap))
+        launch_attract_step_staged<T>(ctx, sa, dim_, group);
+      else
+        launch_attract_step<T>(ctx, sa, dim_, group, false);
       stepped_ = update;
     }
     if (prof_) {
@@ -899,6 +1155,8 @@ class FlatSolverT final : public FlatSolver {
   double avg_deg_ = 0;
   DevBuf<T> mass_, own0_, own1_, Frep_, Fprev_, W_, aos_[2];
   bool use_gather_copy_ = std::getenv("GE_NO_GATHER_COPY") == nullptr;
+  bool staged_step_ = env_int("GE_STEP_STAGED", 1) != 0;
+  bool gather_copy_reordered_ = env_int("GE_GATHER_COPY_REORDERED", 0) != 0;
   bool aos_valid_ = false, stepped_ = false;
   DevBuf<int> rowptr_, J_, perm_;
   std::unique_ptr<RepulsionPlan<T>> rep_;

@@ -112,6 +112,7 @@ class RepulsionSymPlan {
   long long total_units_ = 0, pairs_ = 0;
   DevBuf<SymBlockDesc> blocks_;
   DevBuf<T> partial_, colpartial_;
+  size_t colpartial_elems_ = 0;
 };
 
 // The (row0, row1, tile_first, ntiles, tile_sym0) quintuples of share `part` of `parts` (host).

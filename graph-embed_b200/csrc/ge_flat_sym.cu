@@ -418,7 +418,8 @@ RepulsionSymPlan<T>::RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int 
   blocks_.alloc(ctx, std::max<size_t>(L.blocks.size(), 1));
   blocks_.upload(ctx, L.blocks.data(), L.blocks.size());
   partial_.alloc(ctx, (size_t)grid_ * 2 * dim_ * rb);
-  colpartial_.alloc(ctx, (size_t)std::max<long long>(L.colpartial_elems, 1));
+  colpartial_elems_ = (size_t)std::max<long long>(L.colpartial_elems, 1);
+  colpartial_.alloc(ctx, colpartial_elems_);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
   if (std::getenv("GE_VERBOSE"))
     std::fprintf(stderr,
@@ -430,6 +431,7 @@ RepulsionSymPlan<T>::RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int 
 
 template <typename T>
 void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2) {
+  if (colpartial_.size() == 0) colpartial_.alloc(ctx_, colpartial_elems_);
   RepSymArgs<T> a;
   a.pos = pos;
   a.mass = mass;
