@@ -170,7 +170,7 @@ def workload_config(args):
             "n": args.n, "dim": args.dim, "avg_degree": 10,
             "parallelism": ("single GPU" if args.gpus == 1 else
                             "row-block x%d + coordinate all-gather per iteration" % args.gpus
-                            if getattr(args, "ordered", False) else
+                            if (getattr(args, "ordered", False) or args.n < 32768) else
                             "unordered pairs shared x%d (reduce-scatter of pair sums) + row-block x%d "
                             "attraction/step + coordinate all-gather per iteration" % (args.gpus, args.gpus)),
             "l2": "flushed between timed steps (256 MiB device write outside the timed events)"}
@@ -214,7 +214,7 @@ def run_ours(args):
     # N > 1: symmetric plan -- each rank evaluates 1/N of the unordered pairs over the full length,
     # one reduce-scatter of the pair sums, then attraction + step on its row block, one all-gather
     # of the new coordinates.  --ordered keeps the ordered row-block sweep (no reduce-scatter).
-    sym_ranks = world > 1 and not args.ordered
+    sym_ranks = world > 1 and not args.ordered and n >= 32768  # below: ordered row-block plans
     if sym_ranks:
         plan = ctx.flat_plan(A, dim, params, symmetric=(rank, world))
         assert plan.rows == (r0, r1)
