@@ -731,6 +731,8 @@ const void* cluster_kernel(int L) {
     case 1: return (const void*)k_onchip_cluster<T, D, 1, GA>;
     case 2: return (const void*)k_onchip_cluster<T, D, 2, GA>;
     case 4: return (const void*)k_onchip_cluster<T, D, 4, GA>;
+    case 16: return (const void*)k_onchip_cluster<T, D, 16, GA>;
+    case 32: return (const void*)k_onchip_cluster<T, D, 32, GA>;
     default: return (const void*)k_onchip_cluster<T, D, 8, GA>;
   }
 }
@@ -742,9 +744,13 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   const int per_cta = (n + csize - 1) / csize;
   // measured (tools/profile_small.py k3sweep): 8 lanes per vertex, as in the single-CTA kernel
   // (n = 73: 8 CTAs x 8 lanes 1.3 us/iteration vs 2.2 us on one CTA; n = 157: 1.8 us)
+  // (16 lanes: one trip of the pair loop instead of two up to n = 64 -- 1.11 vs 1.17 us at n = 64,
+  // d = 2; no gain at n = 97, a loss at n = 200; 32 lanes lose everywhere)
   int L = 1;
   while (L < 8 && per_cta * (L * 2) <= 512) L *= 2;
-  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::min(8, std::max(1, std::atoi(v)));
+  if (L == 8 && per_cta * 16 <= 128) L = 16;
+  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::min(32, std::max(1, std::atoi(v)));
+  while (L > 1 && per_cta * L > 512) L /= 2;
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
   GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");
   const bool ga = a.ph.general_attraction != 0;

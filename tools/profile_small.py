@@ -31,13 +31,16 @@ elif mode == "k3sweep":
     import time
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     prec = capi.GE_F32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else capi.GE_F64
-    for target in (34, 54, 97, 200):
+    for target in (34, 54, 64, 97, 200):
         A = graphs.rgg(40 * target, 10.0, seed=1)
         As, Ps = graphs.coarsen(A, 0.25, min_coarse=target)
         Ac = As[-1]
         n = Ac.shape[0]
         x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
-        for cs, L in ((1, 4), (1, 8), (2, 8), (4, 8), (8, 8), (4, 4), (8, 4)):
+        shapes = ((1, 4), (1, 8), (2, 8), (4, 8), (8, 8), (4, 4), (8, 4))
+        if os.environ.get("K3_WIDE"):
+            shapes = ((8, 8), (8, 16), (8, 32), (4, 16), (4, 32))
+        for cs, L in shapes:
             if (n + cs - 1) // cs * L > (1024 if cs == 1 else 512):
                 continue
             os.environ["GE_ONCHIP_LANES"] = str(L)
