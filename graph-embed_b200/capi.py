@@ -69,7 +69,7 @@ SYMBOLS = [
     "ge_flat_plan_sync", "ge_flat_plan_select_kernels", "ge_flat_plan_profile", "ge_flat_plan_profile_get",
     "ge_flat_plan_create_symmetric", "ge_flat_plan_is_symmetric", "ge_flat_plan_pair_sums",
     "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
-    "ge_flat_symmetric_share",
+    "ge_flat_symmetric_share", "ge_galerkin",
 ]
 
 _lib = None
@@ -116,6 +116,11 @@ def _f64(a):
 
 def _ptr(a, typ):
     return None if a is None else a.ctypes.data_as(typ)
+
+
+class GalerkinStats(C.Structure):
+    _fields_ = [("device_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("segments_shared", C.c_int64), ("segments_global", C.c_int64), ("nnz_out", C.c_int64)]
 
 
 class CsrView:
@@ -275,6 +280,25 @@ class Context:
         _check(lib().ge_multilevel_forces(self.h, a.ref(), p.ref(), _ptr(v_A, _pi), _ptr(cA, _pd),
                                           _ptr(x, _pd), int(dim), C.byref(params), _ptr(F, _pd)))
         return F
+
+    def galerkin(self, A, P_T, with_stats=False):
+        """ge_galerkin: A_c = P_T A P_T^T (examples/embedder.cpp:213-216) -> scipy CSR (m x m)."""
+        import scipy.sparse as sp
+        a, pt = CsrView(A), CsrView(P_T, with_data=False)
+        m = P_T.shape[0]
+        cap = max(int(a.indptr[-1]), 1)
+        ptr = np.zeros(m + 1, dtype=np.int32)
+        idx = np.zeros(cap, dtype=np.int32)
+        val = np.zeros(cap)
+        nnz = C.c_int64()
+        st = GalerkinStats()
+        _check(lib().ge_galerkin(self.h, a.ref(), pt.ref(), _ptr(ptr, _pi), _ptr(idx, _pi), _ptr(val, _pd),
+                                 C.c_int64(cap), C.byref(nnz), C.byref(st)))
+        k = int(nnz.value)
+        Ac = sp.csr_matrix((val[:k].copy(), idx[:k].copy(), ptr), shape=(m, m))
+        if with_stats:
+            return Ac, {f: getattr(st, f) for f, _ in st._fields_}
+        return Ac
 
     def flat_plan(self, A, dim, params, rows=None, symmetric=None):
         """rows=(r0, r1): ordered row-block plan; symmetric=(rank, world): that rank's plan of a

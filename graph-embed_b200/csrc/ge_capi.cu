@@ -758,6 +758,19 @@ ge_status ge_level_radii(int m, int dim, double* coords_A, double* r_A, const ge
   });
 }
 
+ge_status ge_galerkin(ge_context* ctx, const ge_csr* A, const ge_csr* P_T, int32_t* c_indptr,
+                      int32_t* c_indices, double* c_data, int64_t capacity, int64_t* nnz_out,
+                      ge_galerkin_stats* stats) {
+  return guarded([&] {
+    require_ctx(ctx);
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(c_indptr && nnz_out, "null argument");
+    *nnz_out = galerkin(ctx, *A, *P_T, c_indptr, c_indices, c_data, capacity, stats);
+    GE_REQUIRE(*nnz_out <= capacity, "output capacity too small (see *nnz_out)");
+  });
+}
+
 void ge_reference_uniform(uint32_t seed, int64_t count, double* out) {
   reference_uniform(seed, count, out);
 }

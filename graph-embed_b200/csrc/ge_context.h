@@ -140,6 +140,10 @@ void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
                       double* pairs_out, int agg_begin = 0, int agg_end = -1);
 
+// ---- ge_galerkin.cu ----------------------------------------------------------------------------
+int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, int32_t* c_indptr,
+                 int32_t* c_indices, double* c_data, int64_t capacity, ge_galerkin_stats* stats);
+
 // ---- ge_capi.cu (host-side level driver) -------------------------------------------------------
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                  const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);

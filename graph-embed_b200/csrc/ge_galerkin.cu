@@ -1,0 +1,353 @@
+// graph-embed_b200 :: Galerkin coarse graph  A_c = P_T * A * P_T^T  on the device (sm_100a).
+//
+// Replaces the step every caller of partition::embed runs before it,
+// /root/reference/examples/embedder.cpp:213-216 and examples/embed.cpp:95-98
+//     As.push_back(P.Mult(As.back()).Mult(P.Transpose()))
+// for an aggregation matrix P_T (m x n, 0/1, one entry per column; row a lists the members of
+// aggregate a).  With such a P_T the product is a relabel-and-merge:
+//     A_c[a][b] = sum of A[i][j] over i in a, j in b            (diagonal entries included, quirk Q5)
+// HBM-bound integer/byte work -- no GEMM, no tensor cores.
+//
+// One CTA per coarse row a ("segment" = the E_a entries of its members' rows, members in P_T
+// order, entries in CSR order):
+//   expand   key = (v_A[j] << 32 | position in the segment), value = A[i][j]
+//   sort     bitonic on the 64-bit keys (shared memory up to 4096 entries, global scratch above)
+//            -> entries ordered by coarse column, ties in member / entry order
+//   reduce   every run of equal coarse columns is summed sequentially in that order (one thread
+//            per run): deterministic, and exactly the order of a row-by-row Gustavson
+//            accumulation; run heads are ranked with a block scan and written to the segment's
+//            slot of a staging buffer, the number of runs is the row length of A_c
+// then the row lengths are scanned on the host (m integers) and k_gal_compact moves the staged
+// rows to their final offsets.  Columns come out ascending within each row.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ge_context.h"
+
+namespace ge {
+
+namespace {
+
+constexpr int kGalSmemMax = 4096;  // largest segment (padded to a power of two) sorted in shared memory
+constexpr unsigned long long kPadKey = ~0ull;
+
+struct GalArgs {
+  const int* I;        // A.indptr  [n+1]
+  const int* J;        // A.indices [nnz]
+  const double* W;     // A.data    [nnz] or nullptr (unit weights)
+  const int* vA;       // vertex -> aggregate [n]
+  const int* Pptr;     // P_T.indptr [m+1]
+  const int* Pidx;     // P_T.indices [n]
+  const int* rowoff;   // offset of fine row i inside its segment [n]
+  const int* segoff;   // first staging slot of segment a [m+1]
+  const int* list;     // segments handled by this launch
+  int* count;          // out: row length of A_c [m]
+  int* tmpcol;         // staging [nnz]
+  double* tmpval;      // staging [nnz]
+  unsigned long long* gkeys;  // big segments: keys scratch (padded sizes, see bigoff)
+  double* gvals;              // big segments: values scratch
+  const long long* bigoff;    // big segments: offset of segment list[b] in gkeys / gvals
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int& total) {
+  // blockDim.x <= 1024, multiple of 32
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += y;
+  }
+  if (lane == 31) scratch[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < nw ? scratch[lane] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, s, off);
+      if (lane >= off) s += y;
+    }
+    scratch[32 + lane] = s;  // inclusive warp totals
+  }
+  __syncthreads();
+  const int base = w > 0 ? scratch[32 + w - 1] : 0;
+  total = scratch[32 + nw - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+// Normalised bitonic network (every compare-exchange ascending; the first step of a merge pairs
+// i with i ^ (2k-1)), so padding keys at the end stay at the end.  N = power of two.
+__device__ __forceinline__ void bitonic_sort(unsigned long long* keys, int N) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+      const int hk = k >> 1;
+      const int lo = (t / hk) * k + (t % hk);
+      const int hi = lo ^ (k - 1);
+      const unsigned long long a = keys[lo], b = keys[hi];
+      if (a > b) {
+        keys[lo] = b;
+        keys[hi] = a;
+      }
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+        const int lo = (t / j) * 2 * j + (t % j);
+        const int hi = lo + j;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if (a > b) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// N: padded segment size of this launch's class (small: shared memory, N <= kGalSmemMax;
+// big: N is read per segment and the arrays live in global scratch).
+template <bool BIG>
+__global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass) {
+  extern __shared__ __align__(16) unsigned char gal_smem[];
+  __shared__ int scan_scratch[64];
+  const int a = g.list[blockIdx.x];
+  const int p0 = g.Pptr[a], p1 = g.Pptr[a + 1];
+  const int s0 = g.segoff[a];
+  const int E = g.segoff[a + 1] - s0;
+  int N = Nclass;
+  unsigned long long* keys;
+  double* vals;
+  if (BIG) {
+    N = 1;
+    while (N < E) N <<= 1;
+    keys = g.gkeys + g.bigoff[blockIdx.x];
+    vals = g.gvals + g.bigoff[blockIdx.x];
+  } else {
+    keys = reinterpret_cast<unsigned long long*>(gal_smem);
+    vals = reinterpret_cast<double*>(gal_smem + (size_t)N * sizeof(unsigned long long));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  // expand: members in P_T order, entries in CSR order
+  for (int mi = p0 + w; mi < p1; mi += nw) {
+    const int i = g.Pidx[mi];
+    const int e0 = g.I[i], len = g.I[i + 1] - e0;
+    const int base = g.rowoff[i];
+    for (int t = lane; t < len; t += 32) {
+      const int e = e0 + t;
+      keys[base + t] = ((unsigned long long)(unsigned)g.vA[g.J[e]] << 32) | (unsigned)(base + t);
+      vals[base + t] = g.W ? g.W[e] : 1.0;
+    }
+  }
+  for (int t = E + threadIdx.x; t < N; t += blockDim.x) keys[t] = kPadKey;
+  __syncthreads();
+  bitonic_sort(keys, N);
+
+  // runs of equal coarse column: rank the heads, sum each run in order
+  int carry = 0;
+  for (int c0 = 0; c0 < E; c0 += blockDim.x) {
+    const int idx = c0 + threadIdx.x;
+    const bool in = idx < E;
+    const unsigned col = in ? (unsigned)(keys[idx] >> 32) : 0u;
+    const bool head = in && (idx == 0 || (unsigned)(keys[idx - 1] >> 32) != col);
+    int total;
+    const int rank = carry + block_exclusive_scan(head ? 1 : 0, scan_scratch, total);
+    if (head) {
+      double sum = 0.0;
+      for (int r = idx; r < E && (unsigned)(keys[r] >> 32) == col; ++r)
+        sum += vals[(unsigned)(keys[r] & 0xffffffffu)];
+      g.tmpcol[s0 + rank] = (int)col;
+      g.tmpval[s0 + rank] = sum;
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) g.count[a] = carry;
+}
+
+// One warp per coarse row: staged row -> final offsets.
+__global__ void __launch_bounds__(256) k_gal_compact(const int* __restrict__ segoff,
+                                                     const int* __restrict__ outptr, int m,
+                                                     const int* __restrict__ tmpcol,
+                                                     const double* __restrict__ tmpval,
+                                                     int* __restrict__ outcol, double* __restrict__ outval) {
+  const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (a >= m) return;
+  const int lane = threadIdx.x & 31;
+  const int s0 = segoff[a], o0 = outptr[a], len = outptr[a + 1] - o0;
+  for (int t = lane; t < len; t += 32) {
+    outcol[o0 + t] = tmpcol[s0 + t];
+    outval[o0 + t] = tmpval[s0 + t];
+  }
+}
+
+}  // namespace
+
+// Returns nnz(A_c); fills c_indptr always, c_indices / c_data when capacity suffices.
+int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_indptr,
+                 int32_t* c_indices, double* c_data, int64_t capacity, ge_galerkin_stats* stats) {
+  const int n = A.rows, m = P.rows;
+  GE_REQUIRE(A.rows == A.cols, "A must be square");
+  GE_REQUIRE(P.cols == n, "P_T.cols != A.rows");
+  GE_REQUIRE(P.indptr[m] == n, "P_T must have exactly one entry per column");
+  const int nnz = A.indptr[n];
+  const double t_begin = now_ms();
+
+  // host: vertex -> aggregate, segment offsets, row offsets inside the segments (O(n))
+  std::vector<int> vA(std::max(n, 1), -1), rowoff(std::max(n, 1), 0), segoff((size_t)m + 1, 0);
+  for (int a = 0; a < m; ++a) {
+    int run = 0;
+    for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) {
+      const int i = P.indices[c];
+      GE_REQUIRE(i >= 0 && i < n && vA[i] < 0, "P_T is not a partition of the vertices");
+      vA[i] = a;
+      rowoff[i] = run;
+      run += A.indptr[i + 1] - A.indptr[i];
+    }
+    segoff[a + 1] = segoff[a] + run;
+  }
+  // size classes: padded power-of-two size 32 .. 4096 in shared memory, larger in global scratch
+  constexpr int kClasses = 8;  // 32, 64, ..., 4096
+  std::vector<int> lists[kClasses], big;
+  std::vector<long long> bigoff;
+  long long big_elems = 0;
+  for (int a = 0; a < m; ++a) {
+    const int E = segoff[a + 1] - segoff[a];
+    if (E == 0) continue;  // count stays 0
+    int N = 32, k = 0;
+    while (N < E && N < kGalSmemMax) {
+      N <<= 1;
+      ++k;
+    }
+    if (E <= kGalSmemMax) {
+      lists[k].push_back(a);
+    } else {
+      long long Np = 1;
+      while (Np < E) Np <<= 1;
+      big.push_back(a);
+      bigoff.push_back(big_elems);
+      big_elems += Np;
+    }
+  }
+  std::vector<int> all_list;
+  int class_begin[kClasses + 1];
+  for (int k = 0; k < kClasses; ++k) {
+    class_begin[k] = (int)all_list.size();
+    all_list.insert(all_list.end(), lists[k].begin(), lists[k].end());
+  }
+  class_begin[kClasses] = (int)all_list.size();
+  const int big_begin = (int)all_list.size();
+  all_list.insert(all_list.end(), big.begin(), big.end());
+
+  const int64_t launches0 = ctx->launches;
+  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1)), d_vA(ctx, std::max(n, 1)),
+      d_Pptr(ctx, m + 1), d_Pidx(ctx, std::max(n, 1)), d_rowoff(ctx, std::max(n, 1)),
+      d_segoff(ctx, m + 1), d_list(ctx, std::max<size_t>(all_list.size(), 1)), d_count(ctx, std::max(m, 1)),
+      d_tmpcol(ctx, std::max(nnz, 1));
+  DevBuf<double> d_W, d_tmpval(ctx, std::max(nnz, 1)), d_gvals(ctx, (size_t)std::max<long long>(big_elems, 1));
+  DevBuf<unsigned long long> d_gkeys(ctx, (size_t)std::max<long long>(big_elems, 1));
+  DevBuf<long long> d_bigoff(ctx, std::max<size_t>(bigoff.size(), 1));
+  d_I.upload(ctx, A.indptr, n + 1);
+  d_J.upload(ctx, A.indices, nnz);
+  if (A.data != nullptr) {
+    d_W.alloc(ctx, std::max(nnz, 1));
+    d_W.upload(ctx, A.data, nnz);
+  }
+  d_vA.upload(ctx, vA.data(), n);
+  d_Pptr.upload(ctx, P.indptr, m + 1);
+  d_Pidx.upload(ctx, P.indices, n);
+  d_rowoff.upload(ctx, rowoff.data(), n);
+  d_segoff.upload(ctx, segoff.data(), m + 1);
+  d_list.upload(ctx, all_list.data(), all_list.size());
+  if (!bigoff.empty()) d_bigoff.upload(ctx, bigoff.data(), bigoff.size());
+  d_count.zero(ctx->stream);
+
+  cudaEvent_t ev0, ev1;
+  GE_CUDA(cudaEventCreate(&ev0));
+  GE_CUDA(cudaEventCreate(&ev1));
+  GE_CUDA(cudaEventRecord(ev0, ctx->stream));
+  GalArgs g;
+  g.I = d_I.get();
+  g.J = d_J.get();
+  g.W = A.data != nullptr ? d_W.get() : nullptr;
+  g.vA = d_vA.get();
+  g.Pptr = d_Pptr.get();
+  g.Pidx = d_Pidx.get();
+  g.rowoff = d_rowoff.get();
+  g.segoff = d_segoff.get();
+  g.count = d_count.get();
+  g.tmpcol = d_tmpcol.get();
+  g.tmpval = d_tmpval.get();
+  g.gkeys = d_gkeys.get();
+  g.gvals = d_gvals.get();
+  g.bigoff = d_bigoff.get();
+  static bool attr_set = false;
+  if (!attr_set) {
+    GE_CUDA(cudaFuncSetAttribute(k_gal_segment<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kGalSmemMax * 16));
+    attr_set = true;
+  }
+  for (int k = 0; k < kClasses; ++k) {
+    const int cnt = class_begin[k + 1] - class_begin[k];
+    if (cnt == 0) continue;
+    const int N = 32 << k;
+    const int threads = std::max(32, std::min(512, N / 2));
+    g.list = d_list.get() + class_begin[k];
+    k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (!big.empty()) {
+    g.list = d_list.get() + big_begin;
+    k_gal_segment<true><<<(unsigned)big.size(), 512, 0, ctx->stream>>>(g, 0);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  // row lengths -> host scan -> final offsets
+  std::vector<int> count(std::max(m, 1), 0);
+  d_count.download(ctx, count.data(), m);
+  GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t total = 0;
+  c_indptr[0] = 0;
+  for (int a = 0; a < m; ++a) {
+    total += count[a];
+    GE_REQUIRE(total < (int64_t)1 << 31, "coarse graph has more than 2^31 entries");
+    c_indptr[a + 1] = (int32_t)total;
+  }
+  if (total <= capacity && total > 0) {
+    GE_REQUIRE(c_indices && c_data, "null output arrays");
+    DevBuf<int> d_outptr(ctx, m + 1), d_outcol(ctx, (size_t)total);
+    DevBuf<double> d_outval(ctx, (size_t)total);
+    d_outptr.upload(ctx, c_indptr, m + 1);
+    const unsigned grid = (unsigned)(((int64_t)m * 32 + 255) / 256);
+    k_gal_compact<<<grid, 256, 0, ctx->stream>>>(d_segoff.get(), d_outptr.get(), m, d_tmpcol.get(),
+                                                 d_tmpval.get(), d_outcol.get(), d_outval.get());
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+    GE_CUDA(cudaEventRecord(ev1, ctx->stream));
+    d_outcol.download(ctx, c_indices, (size_t)total);
+    d_outval.download(ctx, c_data, (size_t)total);
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    GE_CUDA(cudaEventRecord(ev1, ctx->stream));
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (stats) {
+    float ms = 0;
+    GE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats->device_ms = ms;  // kernels + the row-length round trip
+    stats->total_ms = now_ms() - t_begin;
+    stats->kernel_launches = ctx->launches - launches0;
+    stats->segments_shared = big_begin;
+    stats->segments_global = (int64_t)big.size();
+    stats->nnz_out = total;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return total;
+}
+
+}  // namespace ge

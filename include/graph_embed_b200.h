@@ -168,6 +168,28 @@ ge_status ge_multilevel_forces(ge_context* ctx, const ge_csr* A, const ge_csr* P
  * coords_Ac (mc x dim) / r_Ac (mc) = the next-coarser level's rescaled centres and radii. */
 ge_status ge_level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                          const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);
+/* ---- Galerkin coarse graph -------------------------------------- */
+typedef struct ge_galerkin_stats {
+  double device_ms;        /* kernels + the row-length round trip (CUDA events) */
+  double total_ms;         /* whole call, host layout and copies included */
+  int64_t kernel_launches;
+  int64_t segments_shared; /* coarse rows sorted in shared memory */
+  int64_t segments_global; /* coarse rows with more than 4096 fine entries (global scratch) */
+  int64_t nnz_out;
+} ge_galerkin_stats;
+/* A_c = P_T * A * P_T^T, the step examples/embedder.cpp:213-216 (and examples/embed.cpp:95-98)
+ * runs before partition::embed: `As.push_back(P.Mult(As.back()).Mult(P.Transpose()))`.
+ * A: n x n CSR (data may be NULL: unit weights); P_T: m x n aggregation, one entry per column,
+ * row a lists the members of aggregate a (its data is ignored).  Output: m x m CSR with ascending
+ * columns per row, diagonal entries included (the reference keeps them and counts them in the
+ * degree).  c_indptr (m+1) is always filled and *nnz_out set; c_indices / c_data are filled when
+ * capacity >= *nnz_out -- capacity = A->nnz always suffices -- otherwise GE_ERR_INVALID is
+ * returned with *nnz_out set so the caller can retry.  Sums are accumulated in member order, then
+ * CSR entry order (bit-reproducible; unit-weight graphs give integer sums in any order). */
+ge_status ge_galerkin(ge_context* ctx, const ge_csr* A, const ge_csr* P_T, int32_t* c_indptr,
+                      int32_t* c_indices, double* c_data, int64_t capacity, int64_t* nnz_out,
+                      ge_galerkin_stats* stats /* may be NULL */);
+
 /* The reference's random stream: count draws of uniform_real_distribution<double>(-1,1) over
  * std::mt19937(seed) (include/forceatlas.hpp:104-108). */
 void ge_reference_uniform(uint32_t seed, int64_t count, double* out);

@@ -610,3 +610,64 @@ int oracle_embed(int L, const int* An, const int* const* AI, const int* const* A
   free(coords_A);
   return 0;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Galerkin coarse graph, examples/embedder.cpp:213-216 / examples/embed.cpp:95-98:
+ *     As.push_back(P.Mult(As.back()).Mult(P.Transpose()))
+ * for a 0/1 aggregation P (m x n, one entry per column).  linalgcpp (where Mult lives) is not in
+ * the reference tree, so this restates the product itself: A_c[a][b] = sum of A[i][j] over i in a,
+ * j in b, accumulated row by row (members of a in P's order, entries of row i in CSR order) into a
+ * dense accumulator, emitted with ascending columns.  PARITY UNPINNED against linalgcpp's own
+ * summation order; for unit-weight graphs (every BASELINE config) the sums are integers and the
+ * result does not depend on the order.  out_idx / out_val need room for nnz(A) entries.
+ * Returns nnz(A_c). */
+long oracle_galerkin(int n, int m, const int* I, const int* J, const double* D, const int* PI,
+                     const int* PJ, int* out_ptr, int* out_idx, double* out_val) {
+  int* vA = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  double* acc = (double*)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+  int* mark = (int*)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
+  int* cols = (int*)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
+  for (int a = 0; a < m; ++a) {
+    mark[a] = -1;
+    for (int c = PI[a]; c < PI[a + 1]; ++c) vA[PJ[c]] = a;
+  }
+  long nnz = 0;
+  out_ptr[0] = 0;
+  for (int a = 0; a < m; ++a) {
+    int ncols = 0;
+    for (int c = PI[a]; c < PI[a + 1]; ++c) {
+      const int i = PJ[c];
+      for (int e = I[i]; e < I[i + 1]; ++e) {
+        const int b = vA[J[e]];
+        if (mark[b] != a) {
+          mark[b] = a;
+          acc[b] = 0.0;
+          cols[ncols++] = b;
+        }
+        acc[b] += D ? D[e] : 1.0;
+      }
+    }
+    /* ascending columns (insertion sort: rows are short) */
+    for (int x = 1; x < ncols; ++x) {
+      const int v = cols[x];
+      int y = x - 1;
+      while (y >= 0 && cols[y] > v) {
+        cols[y + 1] = cols[y];
+        --y;
+      }
+      cols[y + 1] = v;
+    }
+    for (int x = 0; x < ncols; ++x) {
+      out_idx[nnz] = cols[x];
+      out_val[nnz] = acc[cols[x]];
+      ++nnz;
+    }
+    out_ptr[a + 1] = (int)nnz;
+  }
+  free(vA);
+  free(acc);
+  free(mark);
+  free(cols);
+  return nnz;
+}

@@ -69,7 +69,8 @@ def oracle_lib():
     global _oracle
     if _oracle is None:
         path = os.path.join(HERE, "liboracle.so")
-        if not os.path.exists(path):
+        src = os.path.join(HERE, "forceatlas_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(src) > os.path.getmtime(path):
             build(ref=False)
         _oracle = C.CDLL(path)
         _oracle.oracle_embed.restype = C.c_int
@@ -139,6 +140,21 @@ def radii(coords_A, dim, A_c=None, P_T_c=None, coords_Ac=None, r_Ac=None):
         oracle_lib().oracle_radii(m, dim, _p(cA), _p(rA), _p(AcI), _p(AcJ), P_T_c.shape[0],
                                   _p(PcI), _p(PcJ), _p(cAc), _p(rAc))
     return cA, rA
+
+
+def galerkin(A, P_T):
+    """oracle_galerkin: A_c = P_T A P_T^T (examples/embedder.cpp:213-216) -> scipy CSR."""
+    import scipy.sparse as sp
+    L = oracle_lib()
+    L.oracle_galerkin.restype = C.c_long
+    n, I, J, D = csr_arrays(A)
+    PI, PJ = _i32(P_T.indptr), _i32(P_T.indices)
+    m = P_T.shape[0]
+    ptr = np.zeros(m + 1, dtype=np.int32)
+    idx = np.zeros(max(A.nnz, 1), dtype=np.int32)
+    val = np.zeros(max(A.nnz, 1))
+    nnz = L.oracle_galerkin(n, m, _p(I), _p(J), _p(D), _p(PI), _p(PJ), _p(ptr), _p(idx), _p(val))
+    return sp.csr_matrix((val[:nnz].copy(), idx[:nnz].copy(), ptr), shape=(m, m))
 
 
 def mt_uniform(seed, count):

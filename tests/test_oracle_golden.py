@@ -94,3 +94,22 @@ def test_edge_cases(oracle, graphs):
     x = oracle.multilevel_run(A2, P, cA, np.array([0.7, 0.2]), 2, np.array([[0.1, 0.2], [0.3, -0.4]]),
                               oracle.Params(iterations=100))
     assert np.array_equal(x, cA)
+
+
+def test_galerkin_oracle_matches_scipy_product(oracle, graphs):
+    """oracle_galerkin (examples/embedder.cpp:213-216) against scipy's P_T @ A @ P_T.T: identical
+    structure; identical sums for unit weights, 1e-13 for real weights (summation order)."""
+    import numpy as np
+    A = graphs.rgg(3000, 10.0, seed=1)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=20)
+    for l, P in enumerate(Ps):
+        C = oracle.galerkin(As[l], P)
+        R = graphs.galerkin(As[l], P)
+        assert np.array_equal(C.indptr, R.indptr) and np.array_equal(C.indices, R.indices)
+        assert np.array_equal(C.data, R.data)
+    rng = np.random.default_rng(0)
+    B = As[0].copy()
+    B.data = rng.uniform(0.5, 2.0, B.nnz)
+    C = oracle.galerkin(B, Ps[0])
+    R = graphs.galerkin(B, Ps[0])
+    assert np.array_equal(C.indices, R.indices) and np.abs(C.data - R.data).max() < 1e-12
