@@ -329,6 +329,8 @@ def run_ours(args):
             out["roofline_attraction_large"] = bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src)
         if not args.no_embed:
             out["embed"] = bench_embed(args, capi, ctx, graphs)
+        if not args.no_galerkin:
+            out["galerkin"] = bench_galerkin(args, capi, ctx, graphs, hbm_peak, hbm_src)
         if not args.no_cpu:
             out["cpu_baseline"] = bench_cpu_baseline(args)
     if rank == 0:
@@ -439,6 +441,41 @@ def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
     return out
 
 
+def bench_galerkin(args, capi, ctx, graphs, hbm_peak, hbm_src):
+    """the Galerkin coarse graph P_T A P_T^T (examples/embedder.cpp:213-216)
+    of one level of a 1M-vertex RGG on the device, against its compulsory HBM bytes, next to the
+    oracle's row-by-row accumulation on one host core."""
+    t = time.time()
+    A = graphs.rgg(args.galerkin_n, 10.0, seed=13)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=1000, max_levels=1)
+    P = Ps[0]
+    n, m, nnz = A.shape[0], P.shape[0], A.nnz
+    log("[bench] galerkin level n=%d -> m=%d nnz=%d (%.1fs)" % (n, m, nnz, time.time() - t))
+    ctx.galerkin(A, P)  # warm-up (pool, kernel attributes)
+    best = None
+    for _ in range(3):
+        C, st = ctx.galerkin(A, P, with_stats=True)
+        if best is None or st["device_ms"] < best["device_ms"]:
+            best = st
+    assert np.array_equal(C.indptr, As[1].indptr) and np.array_equal(C.indices, As[1].indices)
+    assert np.array_equal(C.data, As[1].data)
+    b = nnz * 12.0 + n * 16.0 + m * 12.0 + C.nnz * 12.0  # A once, row pointers / maps, A_c once
+    out = {"kernel": "k_gal_segment (+ k_gal_compact)", "bound": "hbm", "unit": "GB/s", "n": n, "m": m,
+           "nnz": nnz, "nnz_out": int(C.nnz), "device_ms": best["device_ms"], "total_ms": best["total_ms"],
+           "bytes": b, "achieved": b / (best["device_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+           "peak_source": hbm_src, "entries_per_sec": nnz / (best["device_ms"] * 1e-3),
+           "segments_shared": best["segments_shared"], "segments_global": best["segments_global"],
+           "kernel_launches": best["kernel_launches"]}
+    out["frac"] = out["achieved"] / hbm_peak
+    if not args.no_cpu:
+        O = entry.load_oracle()
+        t = time.time()
+        O.galerkin(A, P)
+        out["cpu_port_ms"] = 1e3 * (time.time() - t)
+        out["cpu_port_cores"] = 1
+    return out
+
+
 def bench_embed(args, capi, ctx, graphs):
     """BASELINE config 2: embed() wall time, bracketed like examples/embedder.cpp:219-222
     (hierarchy already built, coordinates returned to the host)."""
@@ -513,6 +550,8 @@ def main():
     ap.add_argument("--ordered", action="store_true",
                     help="N > 1: ordered row-block sweep instead of the symmetric pair shares")
     ap.add_argument("--no-embed", action="store_true")
+    ap.add_argument("--no-galerkin", action="store_true")
+    ap.add_argument("--galerkin-n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-attraction", action="store_true")
     args = ap.parse_args()

@@ -17,8 +17,9 @@
 //            per run): deterministic, and exactly the order of a row-by-row Gustavson
 //            accumulation; run heads are ranked with a block scan and written to the segment's
 //            slot of a staging buffer, the number of runs is the row length of A_c
-// then the row lengths are scanned on the host (m integers) and k_gal_compact moves the staged
-// rows to their final offsets.  Columns come out ascending within each row.
+// then the row lengths are scanned on the device and k_gal_compact moves the staged rows to their
+// final offsets.  Segments of up to 128 entries -- the bulk of every hierarchy -- take one warp
+// each (k_gal_warp), larger ones a CTA (k_gal_segment).  Columns come out ascending within each row.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -168,6 +169,122 @@ __global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass
   if (threadIdx.x == 0) g.count[a] = carry;
 }
 
+// Segments of up to 128 entries (the bulk of every hierarchy: a handful of members with ~10
+// entries each): one WARP per segment, eight segments per CTA, warp-synchronous throughout.
+// Same three phases as k_gal_segment.  N = padded size of this launch's class (32, 64 or 128).
+__global__ void __launch_bounds__(256) k_gal_warp(const GalArgs g, int N, int nseg) {
+  extern __shared__ __align__(16) unsigned char gal_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sid = blockIdx.x * 8 + w;
+  if (sid >= nseg) return;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(gal_smem) + (size_t)w * 2 * N;
+  double* vals = reinterpret_cast<double*>(keys + N);
+  const int a = g.list[sid];
+  const int p0 = g.Pptr[a], p1 = g.Pptr[a + 1];
+  const int s0 = g.segoff[a];
+  const int E = g.segoff[a + 1] - s0;
+  constexpr unsigned kFull = 0xffffffffu;
+
+  // expand: 32 members at a time fetch their row descriptors together, then the rows are copied
+  // one after the other with the descriptor broadcast by shuffle
+  for (int m0 = p0; m0 < p1; m0 += 32) {
+    const int cnt = min(32, p1 - m0);
+    int i = 0, e0 = 0, len = 0, base = 0;
+    if (lane < cnt) {
+      i = g.Pidx[m0 + lane];
+      e0 = g.I[i];
+      len = g.I[i + 1] - e0;
+      base = g.rowoff[i];
+    }
+    for (int q = 0; q < cnt; ++q) {
+      const int qe0 = __shfl_sync(kFull, e0, q), qlen = __shfl_sync(kFull, len, q);
+      const int qbase = __shfl_sync(kFull, base, q);
+      for (int t = lane; t < qlen; t += 32) {
+        const int e = qe0 + t;
+        keys[qbase + t] = ((unsigned long long)(unsigned)g.vA[g.J[e]] << 32) | (unsigned)(qbase + t);
+        vals[qbase + t] = g.W ? g.W[e] : 1.0;
+      }
+    }
+  }
+  for (int t = E + lane; t < N; t += 32) keys[t] = kPadKey;
+  __syncwarp();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int t = lane; t < N / 2; t += 32) {
+      const int hk = k >> 1;
+      const int lo = (t / hk) * k + (t % hk);
+      const int hi = lo ^ (k - 1);
+      const unsigned long long x = keys[lo], y = keys[hi];
+      if (x > y) {
+        keys[lo] = y;
+        keys[hi] = x;
+      }
+    }
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = lane; t < N / 2; t += 32) {
+        const int lo = (t / j) * 2 * j + (t % j);
+        const int hi = lo + j;
+        const unsigned long long x = keys[lo], y = keys[hi];
+        if (x > y) {
+          keys[lo] = y;
+          keys[hi] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  int carry = 0;
+  for (int c0 = 0; c0 < E; c0 += 32) {
+    const int idx = c0 + lane;
+    const bool in = idx < E;
+    const unsigned col = in ? (unsigned)(keys[idx] >> 32) : 0u;
+    const bool head = in && (idx == 0 || (unsigned)(keys[idx - 1] >> 32) != col);
+    const unsigned mask = __ballot_sync(kFull, head);
+    if (head) {
+      const int rank = carry + __popc(mask & ((1u << lane) - 1u));
+      double sum = 0.0;
+      for (int r = idx; r < E && (unsigned)(keys[r] >> 32) == col; ++r)
+        sum += vals[(unsigned)(keys[r] & 0xffffffffu)];
+      g.tmpcol[s0 + rank] = (int)col;
+      g.tmpval[s0 + rank] = sum;
+    }
+    carry += __popc(mask);
+  }
+  if (lane == 0) g.count[a] = carry;
+}
+
+// Exclusive scan of the row lengths on the device (three small kernels; m is at most a few million).
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock) k_scan_blocks(const int* __restrict__ in, int n,
+                                                           int* __restrict__ out, int* __restrict__ sums) {
+  __shared__ int scratch[64];
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  const int v = i < n ? in[i] : 0;
+  int total;
+  const int ex = block_exclusive_scan(v, scratch, total);
+  if (i < n) out[i] = ex;
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* sums, int nb) {  // one CTA
+  __shared__ int scratch[64];
+  int carry = 0;
+  for (int c0 = 0; c0 < nb; c0 += kScanBlock) {
+    const int i = c0 + threadIdx.x;
+    const int v = i < nb ? sums[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, total);
+    if (i < nb) sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) sums[nb] = carry;  // grand total
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_add(int* __restrict__ out, int n,
+                                                        const int* __restrict__ sums, int nb) {
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  if (i < n) out[i] += sums[blockIdx.x];
+  if (i == 0) out[n] = sums[nb];
+}
+
 // One warp per coarse row: staged row -> final offsets.
 __global__ void __launch_bounds__(256) k_gal_compact(const int* __restrict__ segoff,
                                                      const int* __restrict__ outptr, int m,
@@ -296,7 +413,10 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
     const int N = 32 << k;
     const int threads = std::max(32, std::min(512, N / 2));
     g.list = d_list.get() + class_begin[k];
-    k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N);
+    if (N <= 128)
+      k_gal_warp<<<(cnt + 7) / 8, 256, (size_t)8 * N * 16, ctx->stream>>>(g, N, cnt);
+    else
+      k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N);
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -306,22 +426,25 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  // row lengths -> host scan -> final offsets
-  std::vector<int> count(std::max(m, 1), 0);
-  d_count.download(ctx, count.data(), m);
-  GE_CUDA(cudaStreamSynchronize(ctx->stream));
-  int64_t total = 0;
-  c_indptr[0] = 0;
-  for (int a = 0; a < m; ++a) {
-    total += count[a];
-    GE_REQUIRE(total < (int64_t)1 << 31, "coarse graph has more than 2^31 entries");
-    c_indptr[a + 1] = (int32_t)total;
+  // row lengths -> exclusive scan on the device -> final offsets (nnz(A_c) <= nnz(A) < 2^31)
+  const int nb = (m + kScanBlock - 1) / kScanBlock;
+  DevBuf<int> d_outptr(ctx, m + 1), d_sums(ctx, nb + 1);
+  if (m > 0) {
+    k_scan_blocks<<<nb, kScanBlock, 0, ctx->stream>>>(d_count.get(), m, d_outptr.get(), d_sums.get());
+    k_scan_sums<<<1, kScanBlock, 0, ctx->stream>>>(d_sums.get(), nb);
+    k_scan_add<<<nb, kScanBlock, 0, ctx->stream>>>(d_outptr.get(), m, d_sums.get(), nb);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+    d_outptr.download(ctx, c_indptr, m + 1);
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    c_indptr[0] = 0;
   }
+  const int64_t total = c_indptr[m];
   if (total <= capacity && total > 0) {
     GE_REQUIRE(c_indices && c_data, "null output arrays");
-    DevBuf<int> d_outptr(ctx, m + 1), d_outcol(ctx, (size_t)total);
+    DevBuf<int> d_outcol(ctx, (size_t)total);
     DevBuf<double> d_outval(ctx, (size_t)total);
-    d_outptr.upload(ctx, c_indptr, m + 1);
     const unsigned grid = (unsigned)(((int64_t)m * 32 + 255) / 256);
     k_gal_compact<<<grid, 256, 0, ctx->stream>>>(d_segoff.get(), d_outptr.get(), m, d_tmpcol.get(),
                                                  d_tmpval.get(), d_outcol.get(), d_outval.get());

@@ -43,6 +43,13 @@ int main(int argc, char** argv) {
     hierarchy.push_back(blocks(nx, ny));
     const SparseMatrix& P = hierarchy.back();
     As.push_back(P.Mult(As.back()).Mult(P.Transpose()));  // examples/embedder.cpp:215
+    // the same product on the device (ge_galerkin) must give the same matrix, entry for entry
+    const SparseMatrix G = ge_b200::galerkin(As[As.size() - 2], P);
+    if (G.GetIndptr() != As.back().GetIndptr() || G.GetIndices() != As.back().GetIndices() ||
+        G.GetData() != As.back().GetData()) {
+      std::cerr << "device Galerkin product differs from P.Mult(A).Mult(P.Transpose())" << std::endl;
+      return 3;
+    }
     nx = (nx + 1) / 2;
     ny = (ny + 1) / 2;
   }

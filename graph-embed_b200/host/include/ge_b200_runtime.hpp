@@ -57,6 +57,21 @@ inline std::vector<std::vector<double>> unflatten(const std::vector<double>& x, 
   return c;
 }
 
+// A_{l+1} = P_T * A_l * P_T^T on the device: the line every caller of partition::embed writes as
+//   As.push_back(P.Mult(As.back()).Mult(P.Transpose()));   (examples/embedder.cpp:213-216)
+// becomes  As.push_back(ge_b200::galerkin(As.back(), P));
+inline SparseMatrix galerkin(const SparseMatrix& A, const SparseMatrix& P_T) {
+  const ge_csr a = view(A), p = view(P_T);
+  std::vector<int> indptr(static_cast<size_t>(P_T.Rows()) + 1), indices(A.GetIndices().size());
+  std::vector<double> data(A.GetIndices().size());
+  int64_t nnz = 0;
+  check(ge_galerkin(default_context(), &a, &p, indptr.data(), indices.data(), data.data(),
+                    static_cast<int64_t>(indices.size()), &nnz, nullptr));
+  indices.resize(static_cast<size_t>(nnz));
+  data.resize(static_cast<size_t>(nnz));
+  return SparseMatrix(std::move(indptr), std::move(indices), std::move(data), P_T.Rows(), P_T.Rows());
+}
+
 // Knobs the reference does not have (precision, seed); change before calling partition::embed.
 struct Options {
   int precision = GE_F64;
