@@ -19,7 +19,9 @@
 //            slot of a staging buffer, the number of runs is the row length of A_c
 // then the row lengths are scanned on the device and k_gal_compact moves the staged rows to their
 // final offsets.  Segments of up to 128 entries -- the bulk of every hierarchy -- take one warp
-// each (k_gal_warp), larger ones a CTA (k_gal_segment).  Columns come out ascending within each row.
+// each (k_gal_warp), larger ones a CTA (k_gal_segment); segments beyond 4096 entries (hub aggregates) are sorted
+// together by a grid-wide segmented bitonic network over global scratch.  Columns come out
+// ascending within each row.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -111,8 +113,10 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* keys, int N) {
 
 // N: padded segment size of this launch's class (small: shared memory, N <= kGalSmemMax;
 // big: N is read per segment and the arrays live in global scratch).
+// phase bits (BIG only; the shared-memory classes always run all three): 1 expand, 2 sort, 4 reduce.
+// Big segments are expanded by their CTA, sorted by the grid-wide network below, then reduced.
 template <bool BIG>
-__global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass) {
+__global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass, int phase) {
   extern __shared__ __align__(16) unsigned char gal_smem[];
   __shared__ int scan_scratch[64];
   const int a = g.list[blockIdx.x];
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass
   unsigned long long* keys;
   double* vals;
   if (BIG) {
-    N = 1;
+    N = 2 * kGalSmemMax;
     while (N < E) N <<= 1;
     keys = g.gkeys + g.bigoff[blockIdx.x];
     vals = g.gvals + g.bigoff[blockIdx.x];
@@ -133,40 +137,141 @@ __global__ void __launch_bounds__(512) k_gal_segment(const GalArgs g, int Nclass
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
-  // expand: members in P_T order, entries in CSR order
-  for (int mi = p0 + w; mi < p1; mi += nw) {
-    const int i = g.Pidx[mi];
-    const int e0 = g.I[i], len = g.I[i + 1] - e0;
-    const int base = g.rowoff[i];
-    for (int t = lane; t < len; t += 32) {
-      const int e = e0 + t;
-      keys[base + t] = ((unsigned long long)(unsigned)g.vA[g.J[e]] << 32) | (unsigned)(base + t);
-      vals[base + t] = g.W ? g.W[e] : 1.0;
+  if (phase & 1) {  // expand: members in P_T order, entries in CSR order
+    for (int mi = p0 + w; mi < p1; mi += nw) {
+      const int i = g.Pidx[mi];
+      const int e0 = g.I[i], len = g.I[i + 1] - e0;
+      const int base = g.rowoff[i];
+      for (int t = lane; t < len; t += 32) {
+        const int e = e0 + t;
+        keys[base + t] = ((unsigned long long)(unsigned)g.vA[g.J[e]] << 32) | (unsigned)(base + t);
+        vals[base + t] = g.W ? g.W[e] : 1.0;
+      }
     }
+    for (int t = E + threadIdx.x; t < N; t += blockDim.x) keys[t] = kPadKey;
+    __syncthreads();
   }
-  for (int t = E + threadIdx.x; t < N; t += blockDim.x) keys[t] = kPadKey;
-  __syncthreads();
-  bitonic_sort(keys, N);
+  if (phase & 2) bitonic_sort(keys, N);
+  if (!(phase & 4)) return;
 
-  // runs of equal coarse column: rank the heads, sum each run in order
+  // runs of equal coarse column: rank the heads, sum each run in order.  A head thread sums runs
+  // of up to kShortRun entries itself; longer runs (a hub aggregate's own column can collect 10^5
+  // entries) are queued and summed by a whole warp: the lanes fetch 32 values at a time, then
+  // every lane adds them in run order through shuffles -- the same sequence of additions, with
+  // the memory latency taken out of the chain.
+  constexpr int kShortRun = 32;
+  __shared__ int q_idx[512], q_rank[512];
+  __shared__ int q_n;
   int carry = 0;
   for (int c0 = 0; c0 < E; c0 += blockDim.x) {
+    if (threadIdx.x == 0) q_n = 0;
     const int idx = c0 + threadIdx.x;
     const bool in = idx < E;
     const unsigned col = in ? (unsigned)(keys[idx] >> 32) : 0u;
     const bool head = in && (idx == 0 || (unsigned)(keys[idx - 1] >> 32) != col);
     int total;
-    const int rank = carry + block_exclusive_scan(head ? 1 : 0, scan_scratch, total);
+    const int rank = carry + block_exclusive_scan(head ? 1 : 0, scan_scratch, total);  // (barriers)
     if (head) {
       double sum = 0.0;
-      for (int r = idx; r < E && (unsigned)(keys[r] >> 32) == col; ++r)
+      int r = idx;
+      for (; r < E && r < idx + kShortRun && (unsigned)(keys[r] >> 32) == col; ++r)
         sum += vals[(unsigned)(keys[r] & 0xffffffffu)];
       g.tmpcol[s0 + rank] = (int)col;
-      g.tmpval[s0 + rank] = sum;
+      if (r < E && r == idx + kShortRun && (unsigned)(keys[r] >> 32) == col) {
+        const int slot = atomicAdd(&q_n, 1);
+        q_idx[slot] = idx;
+        q_rank[slot] = rank;
+      } else {
+        g.tmpval[s0 + rank] = sum;
+      }
     }
+    __syncthreads();
+    for (int q = w; q < q_n; q += nw) {  // one warp per long run
+      const int r0 = q_idx[q];
+      const unsigned qcol = (unsigned)(keys[r0] >> 32);
+      double sum = 0.0;
+      for (int c = r0;; c += 32) {
+        const int r = c + lane;
+        const bool ok = r < E && (unsigned)(keys[r] >> 32) == qcol;
+        const double v = ok ? vals[(unsigned)(keys[r] & 0xffffffffu)] : 0.0;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        const int cnt = __popc(okmask);  // the run is contiguous: ok lanes are 0 .. cnt-1
+        for (int l = 0; l < cnt; ++l) sum += __shfl_sync(0xffffffffu, v, l);
+        if (cnt < 32) break;
+      }
+      if (lane == 0) g.tmpval[s0 + q_rank[q]] = sum;
+    }
+    __syncthreads();
     carry += total;
   }
   if (threadIdx.x == 0) g.count[a] = carry;
+}
+
+// ---- grid-wide segmented bitonic sort for the big segments ------------------------------------
+// Every big segment is padded to a power of two >= 8192, so it consists of whole 1024-key tiles;
+// tileseg[tile] names its segment, segN / segtile0 / segbase the segment's padded size, first tile
+// and first key.  Distances below 1024 are handled inside a tile in shared memory, larger ones by
+// one launch per step over all segments at once (segments shorter than the current merge size
+// sit the step out).
+constexpr int kTileKeys = 1024;
+struct BigSort {
+  unsigned long long* keys;
+  const int* tileseg;
+  const int* segN;
+  const int* segtile0;
+  const long long* segbase;
+};
+__device__ __forceinline__ void cmpx(unsigned long long* k, long long lo, long long hi) {
+  const unsigned long long a = k[lo], b = k[hi];
+  if (a > b) {
+    k[lo] = b;
+    k[hi] = a;
+  }
+}
+// full sort of every 1024-key tile (merge sizes 2 .. 1024)
+__global__ void __launch_bounds__(512) k_bitonic_tile_sort(const BigSort b) {
+  __shared__ unsigned long long t[kTileKeys];
+  unsigned long long* src = b.keys + (long long)blockIdx.x * kTileKeys;
+  for (int i = threadIdx.x; i < kTileKeys; i += 512) t[i] = src[i];
+  __syncthreads();
+  bitonic_sort(t, kTileKeys);
+  for (int i = threadIdx.x; i < kTileKeys; i += 512) src[i] = t[i];
+}
+// one global step of merge size k: flip (j == 0) or half-cleaner at distance j >= 1024
+__global__ void __launch_bounds__(256) k_bitonic_global(const BigSort b, int k, int j) {
+  const long long gp = (long long)blockIdx.x * 256 + threadIdx.x;  // pair index over all tiles
+  const int tile = (int)(gp / (kTileKeys / 2));
+  const int seg = b.tileseg[tile];
+  if (k > b.segN[seg]) return;
+  const long long q = (long long)(tile - b.segtile0[seg]) * (kTileKeys / 2) + gp % (kTileKeys / 2);
+  unsigned long long* keys = b.keys + b.segbase[seg];
+  if (j == 0) {
+    const long long hk = k >> 1;
+    const long long lo = (q / hk) * k + (q % hk);
+    cmpx(keys, lo, lo ^ (long long)(k - 1));
+  } else {
+    const long long lo = (q / j) * 2 * j + (q % j);
+    cmpx(keys, lo, lo + j);
+  }
+}
+// the half-cleaners at distances 512 .. 1 of merge size k, inside each tile
+__global__ void __launch_bounds__(512) k_bitonic_tile_merge(const BigSort b, int k) {
+  __shared__ unsigned long long t[kTileKeys];
+  const int seg = b.tileseg[blockIdx.x];
+  if (k > b.segN[seg]) return;
+  unsigned long long* src = b.keys + (long long)blockIdx.x * kTileKeys;
+  for (int i = threadIdx.x; i < kTileKeys; i += 512) t[i] = src[i];
+  __syncthreads();
+  for (int j = kTileKeys / 2; j > 0; j >>= 1) {
+    const int lo = (threadIdx.x / j) * 2 * j + (threadIdx.x % j);
+    const unsigned long long a = t[lo], c = t[lo + j];
+    if (a > c) {
+      t[lo] = c;
+      t[lo + j] = a;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kTileKeys; i += 512) src[i] = t[i];
 }
 
 // Segments of up to 128 entries (the bulk of every hierarchy: a handful of members with ~10
@@ -330,6 +435,7 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   constexpr int kClasses = 8;  // 32, 64, ..., 4096
   std::vector<int> lists[kClasses], big;
   std::vector<long long> bigoff;
+  std::vector<int> bigN;
   long long big_elems = 0;
   for (int a = 0; a < m; ++a) {
     const int E = segoff[a + 1] - segoff[a];
@@ -342,10 +448,11 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
     if (E <= kGalSmemMax) {
       lists[k].push_back(a);
     } else {
-      long long Np = 1;
+      long long Np = 2 * kGalSmemMax;  // whole 1024-key tiles for the grid-wide sort
       while (Np < E) Np <<= 1;
       big.push_back(a);
       bigoff.push_back(big_elems);
+      bigN.push_back((int)Np);
       big_elems += Np;
     }
   }
@@ -382,6 +489,16 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   if (!bigoff.empty()) d_bigoff.upload(ctx, bigoff.data(), bigoff.size());
   d_count.zero(ctx->stream);
 
+  const bool verbose = std::getenv("GE_VERBOSE") != nullptr;
+  double t_mark = now_ms();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double t = now_ms();
+    std::fprintf(stderr, "[ge] galerkin n=%d %-22s %9.3f ms\n", n, what, t - t_mark);
+    t_mark = t;
+  };
+  lap("layout + upload");
   cudaEvent_t ev0, ev1;
   GE_CUDA(cudaEventCreate(&ev0));
   GE_CUDA(cudaEventCreate(&ev1));
@@ -416,15 +533,55 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
     if (N <= 128)
       k_gal_warp<<<(cnt + 7) / 8, 256, (size_t)8 * N * 16, ctx->stream>>>(g, N, cnt);
     else
-      k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N);
+      k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N, 7);
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
   }
+  lap("shared-memory segments");
+  DevBuf<int> d_tileseg, d_segN, d_segtile0;
   if (!big.empty()) {
     g.list = d_list.get() + big_begin;
-    k_gal_segment<true><<<(unsigned)big.size(), 512, 0, ctx->stream>>>(g, 0);
+    const int ntiles = (int)(big_elems / kTileKeys);
+    std::vector<int> tileseg((size_t)ntiles), segtile0(big.size());
+    int maxN = 0;
+    for (size_t b = 0; b < big.size(); ++b) {
+      segtile0[b] = (int)(bigoff[b] / kTileKeys);
+      for (int t = 0; t < bigN[b] / kTileKeys; ++t) tileseg[(size_t)segtile0[b] + t] = (int)b;
+      maxN = std::max(maxN, bigN[b]);
+    }
+    d_tileseg.alloc(ctx, tileseg.size());
+    d_segN.alloc(ctx, big.size());
+    d_segtile0.alloc(ctx, big.size());
+    d_tileseg.upload(ctx, tileseg.data(), tileseg.size());
+    d_segN.upload(ctx, bigN.data(), big.size());
+    d_segtile0.upload(ctx, segtile0.data(), big.size());
+    BigSort bs;
+    bs.keys = d_gkeys.get();
+    bs.tileseg = d_tileseg.get();
+    bs.segN = d_segN.get();
+    bs.segtile0 = d_segtile0.get();
+    bs.segbase = d_bigoff.get();
+    lap("big: tables");
+    k_gal_segment<true><<<(unsigned)big.size(), 512, 0, ctx->stream>>>(g, 0, 1);  // expand + pad
+    lap("big: expand");
+    k_bitonic_tile_sort<<<ntiles, 512, 0, ctx->stream>>>(bs);
+    ctx->launches += 2;
+    const unsigned pair_grid = (unsigned)((long long)ntiles * (kTileKeys / 2) / 256);
+    for (int k = 2 * kTileKeys; k <= maxN; k <<= 1) {
+      k_bitonic_global<<<pair_grid, 256, 0, ctx->stream>>>(bs, k, 0);
+      ctx->launches++;
+      for (int j = k >> 2; j >= kTileKeys; j >>= 1) {
+        k_bitonic_global<<<pair_grid, 256, 0, ctx->stream>>>(bs, k, j);
+        ctx->launches++;
+      }
+      k_bitonic_tile_merge<<<ntiles, 512, 0, ctx->stream>>>(bs, k);
+      ctx->launches++;
+    }
+    lap("big: sort");
+    k_gal_segment<true><<<(unsigned)big.size(), 512, 0, ctx->stream>>>(g, 0, 4);  // reduce the runs
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
+    lap("big: reduce");
   }
   // row lengths -> exclusive scan on the device -> final offsets (nnz(A_c) <= nnz(A) < 2^31)
   const int nb = (m + kScanBlock - 1) / kScanBlock;
@@ -440,6 +597,7 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   } else {
     c_indptr[0] = 0;
   }
+  lap("scan + row pointers");
   const int64_t total = c_indptr[m];
   if (total <= capacity && total > 0) {
     GE_REQUIRE(c_indices && c_data, "null output arrays");

@@ -109,3 +109,17 @@ def test_embed_on_gpu_built_hierarchy_matches_host_built(ctx, capi, graphs):
     x1, _ = ctx.embed(Gs, Ps, 2, seed=5, coarse_iterations=500)
     x2, _ = ctx.embed(As, Ps, 2, seed=5, coarse_iterations=500)
     assert np.array_equal(x1, x2)
+
+
+@pytest.mark.parametrize("n", [1500, 4000])   # shared-memory segments / global-scratch segments
+def test_long_runs_keep_the_sequential_summation_order(ctx, oracle, graphs, n):
+    """Five aggregates: every coarse row merges hundreds of entries per column.  Runs longer than
+    32 entries are summed by a warp (values fetched in parallel, added in run order): the result
+    must still be the sequential sum, bit for bit, with real weights."""
+    rng = np.random.default_rng(21)
+    A = graphs.rgg(n, 10.0, seed=23).tocsr()
+    A.data = rng.uniform(0.1, 3.0, A.nnz)
+    P = _random_partition(A.shape[0], 5, rng)
+    C, st = ctx.galerkin(A, P, with_stats=True)
+    assert (st["segments_global"] > 0) == (n > 2500)
+    _same(C, oracle.galerkin(A, P))
