@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libgraphembed_b200.so")
+# GE_LIB: an alternative build of the same library (kernel experiments: tools/sweep_*.py)
+LIB_PATH = os.environ.get("GE_LIB") or os.path.join(PKG, "lib", "libgraphembed_b200.so")
 
 GE_OK, GE_ERR_INVALID, GE_ERR_NO_DEVICE, GE_ERR_CUDA, GE_ERR_OOM, GE_ERR_UNSUPPORTED = range(6)
 GE_F64, GE_F32 = 0, 1
