@@ -430,6 +430,73 @@ struct EmbedRun {
   ge_embed_stats st{};
   double* final_out = nullptr;  // level 0 is written straight into the caller's buffer
 
+  // The level graphs are inputs that do not depend on any result: a helper thread uploads the
+  // large ones on the copy stream while the coarsest-level solve (one long kernel that needs no
+  // host attention) occupies the main stream.
+  std::vector<std::unique_ptr<PrefetchedGraph>> pre;
+  std::thread prefetcher;
+  std::string prefetch_error;
+  ge_status prefetch_status = GE_OK;
+  double prefetch_h2d = 0.0;
+  static constexpr int64_t kPrefetchMinNnz = 1 << 18;
+
+  void start_prefetch() {
+    pre.resize(L);
+    bool any = false;
+    for (int l = 0; l < L; ++l) any = any || As[l].nnz >= kPrefetchMinNnz;
+    if (!any || std::getenv("GE_NO_PREFETCH")) return;
+    if (!ctx->copy_stream) GE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    prefetcher = std::thread([this] {
+      try {
+        GE_CUDA(cudaSetDevice(ctx->device));
+        ge_context side = *ctx;  // same device and pool, its own stream / staging ring / counters
+        side.stream = ctx->copy_stream;
+        side.stager = ctx->stager2;
+        side.h2d_bytes = 0;
+        for (int l = 0; l < L; ++l) {  // finest first: it is the largest and the last one needed
+          const ge_csr& A = As[l];
+          if (A.nnz < kPrefetchMinNnz) continue;
+          std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
+          g->I.alloc(&side, A.rows + 1);
+          g->J.alloc(&side, (size_t)A.nnz);
+          g->I.upload(&side, A.indptr, A.rows + 1);
+          g->J.upload(&side, A.indices, (size_t)A.nnz);
+          if (A.data != nullptr) {
+            g->Dw.alloc(&side, (size_t)A.nnz);
+            g->Dw.upload(&side, A.data, (size_t)A.nnz);
+          }
+          GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
+          GE_CUDA(cudaEventRecord(g->ready, side.stream));
+          pre[l] = std::move(g);
+        }
+        ctx->stager2 = side.stager;  // keep the ring for the next call
+        prefetch_h2d = side.h2d_bytes;
+      } catch (const Fail& f) {
+        prefetch_status = f.st;
+        prefetch_error = ge_last_error();
+      } catch (const std::exception& e) {
+        prefetch_status = GE_ERR_INVALID;
+        prefetch_error = e.what();
+      }
+    });
+  }
+  void join_prefetch() {
+    if (!prefetcher.joinable()) return;
+    prefetcher.join();
+    ctx->h2d_bytes += prefetch_h2d;
+    prefetch_h2d = 0.0;
+    if (prefetch_status != GE_OK) {
+      set_error("level-graph prefetch: " + prefetch_error);
+      throw Fail{prefetch_status};
+    }
+  }
+  ~EmbedRun() {
+    if (prefetcher.joinable()) prefetcher.join();
+    // the prefetched buffers were allocated on the copy stream: nothing on the main stream may
+    // still read them when they are returned to the pool
+    if (!pre.empty()) cudaStreamSynchronize(ctx->stream);
+  }
+
   // embedMultilevel, src/embed.cpp:576-796.  Returns this level's coordinates; r_A / coords_A
   // receive the radii and (rescaled) coordinates of level+1, as the reference's out-params do.
   std::vector<double> level(int l, std::vector<double>& r_A, std::vector<double>& coords_A) {
@@ -448,6 +515,7 @@ struct EmbedRun {
       const double t0 = now_ms();
       flat_solve(ctx, A, dim, coords.data(), p, 0);
       st.coarse_ms += now_ms() - t0;
+      join_prefetch();  // normally long finished: the solve above takes 0.1-0.2 s
       st.pair_interactions += double(n) * double(n - 1) * p.iterations;
       st.edge_visits += double(A.nnz) * p.iterations;
       return coords;
@@ -488,7 +556,7 @@ struct EmbedRun {
     double pairs = 0.0;
     multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(),
                      init.empty() ? nullptr : init.data(), direct ? final_out : coords.data(), dim, p,
-                     false, &pairs);
+                     false, &pairs, 0, -1, (size_t)l < pre.size() ? pre[l].get() : nullptr);
     st.levels_ms += now_ms() - t1;
     st.pair_interactions += pairs * p.iterations;
     st.edge_visits += double(A.nnz) * p.iterations;
@@ -603,6 +671,9 @@ void ge_context_destroy(ge_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     delete ctx->stager;
   }
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  delete ctx->stager2;
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -697,6 +768,7 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     const double t0 = now_ms();
     std::vector<double> r_A, coords_A;
     run.final_out = n_levels > 0 ? coords_out : nullptr;
+    run.start_prefetch();
     std::vector<double> coords = run.level(0, r_A, coords_A);
     if (!coords.empty()) std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
     if (r_A_out && !r_A.empty()) std::memcpy(r_A_out, r_A.data(), r_A.size() * sizeof(double));

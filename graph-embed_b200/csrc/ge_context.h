@@ -17,6 +17,10 @@ struct Stager;  // pinned staging ring for large host->device copies (ge_capi.cu
 
 struct ge_context {
   ge::Stager* stager = nullptr;
+  // second stream + staging ring: ge_embed uploads the level graphs on it from a helper thread
+  // while the coarsest-level solve occupies the main stream
+  cudaStream_t copy_stream = nullptr;
+  ge::Stager* stager2 = nullptr;
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -135,10 +139,21 @@ void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_param
                        bool forces_only);
 
 // ---- ge_multilevel.cu ------------------------------------------------------------------------
+// A level graph already on the device (uploaded ahead of time on another stream); `ready` is
+// recorded after the last copy.
+struct PrefetchedGraph {
+  DevBuf<int> I, J;
+  DevBuf<double> Dw;  // empty when A.data == nullptr
+  cudaEvent_t ready = nullptr;
+  ~PrefetchedGraph() {
+    if (ready) cudaEventDestroy(ready);
+  }
+};
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
-                      double* pairs_out, int agg_begin = 0, int agg_end = -1);
+                      double* pairs_out, int agg_begin = 0, int agg_end = -1,
+                      const PrefetchedGraph* pre = nullptr);
 
 // ---- ge_galerkin.cu ----------------------------------------------------------------------------
 int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, int32_t* c_indptr,

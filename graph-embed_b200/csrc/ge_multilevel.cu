@@ -241,7 +241,7 @@ template <typename T>
 void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
                   const double* coords_A, const double* r_A, const double* init,
                   double* coords_out, int dim, const ge_params& p, bool forces_only,
-                  double* pairs_out, int agg_begin, int agg_end) {
+                  double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
   constexpr int NM = Real<T>::kMassArrays;
   const int n = A.rows, m = P.rows;
   const int nnz = A.indptr[n];
@@ -337,14 +337,29 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 
   lap("host layout");
   // ---- upload ------------------------------------------------------------------------------
-  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1)), d_vA(ctx, std::max(n, 1)), d_vtx(ctx, (size_t)ld), d_slot_of(ctx, std::max(n, 1)), d_agg_base(ctx, std::max(m, 1)), d_agg_of_slot(ctx, (size_t)ld), d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
+  DevBuf<int> d_I, d_J, d_vA(ctx, std::max(n, 1)), d_vtx(ctx, (size_t)ld), d_slot_of(ctx, std::max(n, 1)), d_agg_base(ctx, std::max(m, 1)), d_agg_of_slot(ctx, (size_t)ld), d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
   DevBuf<double> d_Dw, d_cA(ctx, (size_t)std::max(m, 1) * dim), d_rA(ctx, std::max(m, 1)), d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
   DevBuf<T> d_mass(ctx, (size_t)NM * ld), d_E(ctx, (size_t)dim * ld), d_ew;
-  d_I.upload(ctx, A.indptr, n + 1);
-  d_J.upload(ctx, A.indices, nnz);
-  if (A.data != nullptr) {
-    d_Dw.alloc(ctx, std::max(nnz, 1));
-    d_Dw.upload(ctx, A.data, nnz);
+  const int* dI;
+  const int* dJ;
+  const double* dDw = nullptr;
+  if (pre != nullptr) {  // the graph was uploaded ahead of time on the copy stream
+    GE_CUDA(cudaStreamWaitEvent(ctx->stream, pre->ready, 0));
+    dI = pre->I.get();
+    dJ = pre->J.get();
+    if (A.data != nullptr) dDw = pre->Dw.get();
+  } else {
+    d_I.alloc(ctx, n + 1);
+    d_J.alloc(ctx, std::max(nnz, 1));
+    d_I.upload(ctx, A.indptr, n + 1);
+    d_J.upload(ctx, A.indices, nnz);
+    if (A.data != nullptr) {
+      d_Dw.alloc(ctx, std::max(nnz, 1));
+      d_Dw.upload(ctx, A.data, nnz);
+      dDw = d_Dw.get();
+    }
+    dI = d_I.get();
+    dJ = d_J.get();
   }
   if (weighted) d_ew.alloc(ctx, std::max(nnz, 1));
   d_vA.upload(ctx, v_A, n);
@@ -370,9 +385,9 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   lap("upload");
   // ---- prep --------------------------------------------------------------------------------
   PrepArgs<T> pa;
-  pa.I = d_I.get();
-  pa.J = d_J.get();
-  pa.Dw = A.data != nullptr ? d_Dw.get() : nullptr;
+  pa.I = dI;
+  pa.J = dJ;
+  pa.Dw = dDw;
   pa.v_A = d_vA.get();
   pa.vtx = d_vtx.get();
   pa.slot_of = d_slot_of.get();
@@ -518,7 +533,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
-                      double* pairs_out, int agg_begin, int agg_end) {
+                      double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
   if (agg_end < 0) agg_end = P_T.rows;
   GE_REQUIRE(0 <= agg_begin && agg_begin <= agg_end && agg_end <= P_T.rows, "bad aggregate range");
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
@@ -526,9 +541,9 @@ void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const
   GE_REQUIRE(P_T.cols == A.rows, "P_T.cols must equal A.rows");
   GE_REQUIRE(P_T.indptr[P_T.rows] == A.rows, "P_T must list every vertex exactly once");
   if (p.precision == GE_F32)
-    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end);
+    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre);
   else
-    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end);
+    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre);
 }
 
 }  // namespace ge
