@@ -438,7 +438,7 @@ struct EmbedRun {
   std::string prefetch_error;
   ge_status prefetch_status = GE_OK;
   double prefetch_h2d = 0.0;
-  static constexpr int64_t kPrefetchMinNnz = 1 << 18;
+  static constexpr int64_t kPrefetchMinNnz = 1 << 22;  // ~50 MB of CSR: below, the upload is < 2 ms
 
   void start_prefetch() {
     pre.resize(L);

@@ -20,7 +20,6 @@
 #include <cooperative_groups.h>
 
 #include "ge_onchip.cuh"
-#include "ge_tma.cuh"
 
 namespace ge {
 
@@ -321,7 +320,6 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
   __shared__ double bc[D + 1];
-  __shared__ __align__(8) uint64_t xbar[2];  // one per position buffer: counts the bytes peers store
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
 
@@ -360,11 +358,6 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
     }
   }
   for (int i = tid; i < 2 * S * DP + S * MP; i += blockDim.x) pos[i] = (T)0;
-  if (tid == 0) {
-    mbar_init(&xbar[0], 1);
-    mbar_init(&xbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
   for (int i = tid; i < s; i += blockDim.x) {  // every CTA loads the whole graph's state
 #pragma unroll
@@ -379,14 +372,7 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
   const T* pc = pos;
   T* pn = pos + S * DP;
   int nxt = 1;
-  // The exchange: every owner stores its new position into the NEXT buffer of every CTA with
-  // st.async, which counts the bytes on that CTA's mbarrier for the buffer; a CTA starts the next
-  // iteration when its own barrier has seen all s * D values.  No cluster-wide barrier: a peer can
-  // only overwrite a buffer after it has received this CTA's results of the iteration that read it.
-  const uint32_t xbytes = (uint32_t)(s * D * sizeof(T));
-  const bool use_xbar = a.cluster_exchange != 0;
   for (int it = 0; it < a.iters; ++it) {
-    if (use_xbar && tid == 0) mbar_expect_tx(&xbar[nxt], xbytes);
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
@@ -459,34 +445,20 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
       for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
     }
     if (!(a.debug_skip & 2)) vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
-    if (use_xbar) {
-      if (owner) {  // the L lanes of the group share out the csize peer stores
-        const T* slot_next = pos + (size_t)nxt * S * DP + (size_t)gv * DP;
-        for (int rr = part; rr < csize; rr += L) {
-          const uint32_t dst = mapa_rank(slot_next, (uint32_t)rr);
-          const uint32_t bar = mapa_rank(&xbar[nxt], (uint32_t)rr);
+    if (owner) {  // the L lanes of the group share out the csize peer stores
+      for (int rr = part; rr < csize; rr += L) {
+        T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
 #pragma unroll
-          for (int k = 0; k < D; ++k) st_async(dst + (uint32_t)(k * sizeof(T)), x[k], bar);
-        }
+        for (int k = 0; k < D; ++k) dst[k] = x[k];
       }
-      mbar_wait_cluster(&xbar[nxt], (uint32_t)(it >> 1) & 1u);
-    } else {
-      if (owner) {
-        for (int rr = part; rr < csize; rr += L) {
-          T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
-#pragma unroll
-          for (int k = 0; k < D; ++k) dst[k] = x[k];
-        }
-      }
-      cluster.sync();
     }
+    cluster.sync();
     const T* tmp = pc;
     pc = pn;
     pn = const_cast<T*>(tmp);
     nxt ^= 1;
   }
 
-  if (use_xbar) cluster.sync();  // no CTA leaves while a peer may still store into its shared memory
   if (!a.normalize) {
     if (owner && part == 0) {
 #pragma unroll
@@ -850,7 +822,6 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   a.normalize = p.normalize;
   a.ph = make_physics<T>(p);
   if (const char* v = std::getenv("GE_ONCHIP_SKIP")) a.debug_skip = std::atoi(v);
-  if (const char* v = std::getenv("GE_CLUSTER_XBAR")) a.cluster_exchange = std::atoi(v);
   // Larger coarsest levels are spread over a thread-block cluster (measured crossover n ~ 40).
   int csize = 1;
   if (!forces_only) {

@@ -29,7 +29,6 @@ struct OnchipArgs {
   double* out_aos = nullptr;         // [n][D] final coordinates (or forces when forces_only)
   int iters = 0;
   int forces_only = 0;
-  int cluster_exchange = 0;          // cluster solve: 0 = plain DSMEM stores + cluster barrier, 1 (GE_CLUSTER_XBAR) = st.async + per-buffer mbarriers (measured equal)
   int debug_skip = 0;                // measurement only (GE_ONCHIP_SKIP): 1 = no pair loop, 2 = no epilogue, 4 = no barrier
   int normalize = 0;                 // flat epilogue of include/forceatlas.hpp:272-303
   Physics<T> ph;

@@ -49,46 +49,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       : "memory");
 }
 
-// ---- distributed shared memory: remote stores that signal the destination CTA's mbarrier ------
-// shared::cluster address of `p` (an address in this CTA's shared memory) in CTA `rank`
-__device__ __forceinline__ uint32_t mapa_rank(const void* p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(rank));
-  return r;
-}
-// Asynchronous store into a peer's shared memory; counts sizeof(value) bytes on the peer's mbarrier
-// when the data has landed (the peer sees it after observing the phase completion).
-__device__ __forceinline__ void st_async(uint32_t remote_addr, double v, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
-                   remote_addr),
-               "l"(__double_as_longlong(v)), "r"(remote_bar)
-               : "memory");
-}
-__device__ __forceinline__ void st_async(uint32_t remote_addr, float v, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
-                   remote_addr),
-               "r"(__float_as_uint(v)), "r"(remote_bar)
-               : "memory");
-}
-// Wait with cluster-scope acquire (data written by peers); bounded like mbar_wait.
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_addr(bar);
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-
 template <typename T, int VEC>
 struct VecLoad;
 template <>
