@@ -280,6 +280,21 @@ def ref_radii_case(As, P_Ts, dim, seed, kind="strict"):
                 coords_A_out=cA_out, r_A_out=rA_out)
 
 
+def ref_galerkin(A, P_T, kind="strict"):
+    """examples/embedder.cpp:215 through the compiled reference driver (stand-in linalgcpp)."""
+    import scipy.sparse as sp
+    L = ref_lib(kind)
+    L.ref_galerkin.restype = C.c_long
+    n, I, J, D = csr_arrays(A)
+    PI, PJ = _i32(P_T.indptr), _i32(P_T.indices)
+    m = P_T.shape[0]
+    ptr = np.zeros(m + 1, dtype=np.int32)
+    idx = np.zeros(max(A.nnz, 1), dtype=np.int32)
+    val = np.zeros(max(A.nnz, 1))
+    nnz = L.ref_galerkin(n, _p(I), _p(J), _p(D), m, _p(PI), _p(PJ), _p(ptr), _p(idx), _p(val))
+    return sp.csr_matrix((val[:nnz].copy(), idx[:nnz].copy(), ptr), shape=(m, m))
+
+
 def ref_partition(A, coarsening_factor, matching_iterations=2, nthreads=8, kind="fast"):
     """partition::partition(A, cf, false, true, 1.0, matchingIterations, false) -> [P_T csr]."""
     import scipy.sparse as sp

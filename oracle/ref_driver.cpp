@@ -159,6 +159,23 @@ int ref_radii_case(int L, const int* An, const int* const* AI, const int* const*
 // partition::partition(A, coarseningFactor, false, true, 1.0, matchingIterations, false)
 // (call shape of examples/embedder.cpp:187).  Returns the number of levels; the
 // P_T matrices are fetched with ref_hierarchy_rows / ref_hierarchy_get.
+// The caller-side line examples/embedder.cpp:215, `P.Mult(A).Mult(P.Transpose())`, evaluated with
+// the stand-in linalgcpp container (host/compat/sparsematrix.hpp: row-wise Gustavson product,
+// ascending columns).  Returns nnz; out_idx / out_val need room for nnz(A) entries.
+long ref_galerkin(int n, const int* I, const int* J, const double* D, int m, const int* PI,
+                  const int* PJ, int* out_ptr, int* out_idx, double* out_val) {
+  const int nnz = I[n];
+  SparseMatrix A(std::vector<int>(I, I + n + 1), std::vector<int>(J, J + nnz),
+                 std::vector<double>(D, D + nnz), n, n);
+  SparseMatrix P(std::vector<int>(PI, PI + m + 1), std::vector<int>(PJ, PJ + n),
+                 std::vector<double>(n, 1.0), m, n);
+  const SparseMatrix C = P.Mult(A).Mult(P.Transpose());
+  std::memcpy(out_ptr, C.GetIndptr().data(), sizeof(int) * (m + 1));
+  std::memcpy(out_idx, C.GetIndices().data(), sizeof(int) * C.GetIndices().size());
+  std::memcpy(out_val, C.GetData().data(), sizeof(double) * C.GetData().size());
+  return (long)C.GetIndices().size();
+}
+
 int ref_partition(int n, const int* I, const int* J, const double* D, double coarseningFactor,
                   int matchingIterations, int nthreads) {
   omp_set_num_threads(nthreads);

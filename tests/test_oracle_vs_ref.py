@@ -47,3 +47,21 @@ def test_multilevel_and_embed_with_own_hierarchy(ref, graphs):
         assert np.array_equal(xo, ref.ref_multilevel(As[l], Ps[l], cA, rA, 3, p, seed=8))
     xr, _ = ref.ref_embed(As, Ps, 2, seed=13)
     assert np.array_equal(ref.embed(As, Ps, 2, seed=13), xr)
+
+
+def test_galerkin_matches_the_callers_expression(ref, graphs):
+    """oracle_galerkin against `P.Mult(A).Mult(P.Transpose())` (examples/embedder.cpp:215) run
+    through the reference driver with the stand-in linalgcpp container: same structure; identical
+    sums on unit-weight graphs (integers) and on every coarser level; real weights agree to
+    rounding (the two-stage product associates the sums differently)."""
+    A = graphs.rgg(2500, 10.0, seed=6)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=20)
+    for l, P in enumerate(Ps):
+        C, R = ref.galerkin(As[l], P), ref.ref_galerkin(As[l], P)
+        assert np.array_equal(C.indptr, R.indptr) and np.array_equal(C.indices, R.indices)
+        assert np.array_equal(C.data, R.data)
+    B = As[0].copy()
+    B.data = np.random.default_rng(1).uniform(0.5, 2.0, B.nnz)
+    C, R = ref.galerkin(B, Ps[0]), ref.ref_galerkin(B, Ps[0])
+    assert np.array_equal(C.indices, R.indices)
+    assert np.abs(C.data - R.data).max() < 1e-12
