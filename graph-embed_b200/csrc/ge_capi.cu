@@ -465,6 +465,7 @@ struct EmbedRun {
             g->Dw.alloc(&side, (size_t)A.nnz);
             g->Dw.upload(&side, A.data, (size_t)A.nnz);
           }
+          g->layout = make_level_layout(&side, Ps[l], A.rows);  // slot layout + its device copies
           GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
           GE_CUDA(cudaEventRecord(g->ready, side.stream));
           pre[l] = std::move(g);
@@ -533,9 +534,13 @@ struct EmbedRun {
       level_radii(m, dim, coords_A.data(), r_A.data(), &As[l + 1], &Ps[l + 1], coords_Ac.data(), r_Ac.data());
     st.host_radii_ms += now_ms() - t0;
 
-    std::vector<int32_t> v_A(n);  // :605
-    for (int a = 0; a < m; ++a)
-      for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) v_A[P.indices[c]] = a;
+    const PrefetchedGraph* pg = (size_t)l < pre.size() ? pre[l].get() : nullptr;
+    std::vector<int32_t> v_A;  // :605 (already on the device when the level was prepared ahead)
+    if (pg == nullptr || pg->layout == nullptr) {
+      v_A.resize(n);
+      for (int a = 0; a < m; ++a)
+        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) v_A[P.indices[c]] = a;
+    }
     // Initial local coordinates: with a fixed seed, the reference's own stream in its draw order
     // (forceatlas.hpp:341, 356-358); with seed 0 (the reference's std::random_device mode, where
     // any stream is as good as another) they are drawn on the device.
@@ -554,9 +559,9 @@ struct EmbedRun {
     std::vector<double> coords(direct ? 0 : (size_t)n * dim);
     const double t1 = now_ms();
     double pairs = 0.0;
-    multilevel_solve(ctx, A, P, v_A.data(), coords_A.data(), r_A.data(),
+    multilevel_solve(ctx, A, P, v_A.empty() ? nullptr : v_A.data(), coords_A.data(), r_A.data(),
                      init.empty() ? nullptr : init.data(), direct ? final_out : coords.data(), dim, p,
-                     false, &pairs, 0, -1, (size_t)l < pre.size() ? pre[l].get() : nullptr);
+                     false, &pairs, 0, -1, pg);
     st.levels_ms += now_ms() - t1;
     st.pair_interactions += pairs * p.iterations;
     st.edge_visits += double(A.nnz) * p.iterations;

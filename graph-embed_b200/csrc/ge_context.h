@@ -141,12 +141,17 @@ void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_param
 // ---- ge_multilevel.cu ------------------------------------------------------------------------
 // A level graph already on the device (uploaded ahead of time on another stream); `ready` is
 // recorded after the last copy.
+struct LevelLayout;  // slot layout of a level (ge_multilevel.cu): depends on P_T only
+LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n);
+void free_level_layout(LevelLayout* layout);
 struct PrefetchedGraph {
   DevBuf<int> I, J;
   DevBuf<double> Dw;  // empty when A.data == nullptr
+  LevelLayout* layout = nullptr;
   cudaEvent_t ready = nullptr;
   ~PrefetchedGraph() {
     if (ready) cudaEventDestroy(ready);
+    free_level_layout(layout);
   }
 };
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
+#include <memory>
 #include <vector>
 
 #include "ge_flat.cuh"
@@ -237,26 +238,35 @@ __global__ void __launch_bounds__(1024) k_ml_segment_epilogue(const T* __restric
   }
 }
 
-template <typename T>
-void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
-                  const double* coords_A, const double* r_A, const double* init,
-                  double* coords_out, int dim, const ge_params& p, bool forces_only,
-                  double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
-  constexpr int NM = Real<T>::kMassArrays;
-  const int n = A.rows, m = P.rows;
-  const int nnz = A.indptr[n];
-  const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
-  const bool weighted = p.use_weights && A.data != nullptr;
 
-  const bool verbose = std::getenv("GE_VERBOSE") != nullptr;
-  double t_mark = now_ms();
-  auto lap = [&](const char* what) {
-    if (!verbose) return;
-    GE_CUDA(cudaStreamSynchronize(ctx->stream));
-    const double t = now_ms();
-    std::fprintf(stderr, "[ge] level n=%d %-18s %8.3f ms\n", n, what, t - t_mark);
-    t_mark = t;
-  };
+// ---------------------------------------------------------------------------------------------
+// Slot layout of one level: depends only on the aggregation P_T (and on the on-chip tier limits),
+// not on any coordinates -- ge_embed builds it ahead of time, on the copy stream, while the
+// coarsest-level solve runs.
+// ---------------------------------------------------------------------------------------------
+struct CtaClass {  // CTA tier: one launch per lanes-per-vertex class (the kernel is specialised on it)
+  std::vector<int4> tasks;
+  int threads = 32, size_max = 1;
+};
+}  // namespace
+
+struct LevelLayout {
+  std::vector<int4> segs, packs;
+  CtaClass cta_class[4];  // L = 1, 2, 4, 8
+  int grid_slots = 0, single_begin = 0, n_single = 0, nslots = 0;
+  int64_t ld = 0;
+  double pairs = 0.0;
+  DevBuf<int> d_vA, d_vtx, d_slot_of, d_agg_base, d_agg_of_slot;
+};
+
+namespace {
+void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* v_A, bool forces_only,
+                        int agg_begin, int agg_end, LevelLayout& L_) {
+  const int m = P.rows;
+  const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
+  std::vector<int4>& segs = L_.segs;
+  std::vector<int4>& packs = L_.packs;
+  CtaClass* cta_class = L_.cta_class;
   // ---- host: bin aggregates by size and lay out the slots -------------------------------------
   std::vector<int> by_size[33];
   std::vector<int> cta_aggs, grid_aggs;
@@ -269,12 +279,11 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     else if (s <= cta_max) cta_aggs.push_back(a);
     else grid_aggs.push_back(a);
   }
-  if (pairs_out) *pairs_out = pairs;
+  L_.pairs = pairs;
   auto size_of = [&](int a) { return P.indptr[a + 1] - P.indptr[a]; };
   std::sort(cta_aggs.begin(), cta_aggs.end(), [&](int x, int y) { return size_of(x) > size_of(y); });
 
   std::vector<int> agg_base(std::max(m, 1), 0);
-  std::vector<int4> segs, packs;
   int64_t cursor = 0;
   for (int a : grid_aggs) {
     const int s = size_of(a);
@@ -282,13 +291,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     segs.push_back(make_int4((int)cursor, s, a, 0));
     cursor = round_up(cursor + s, kTileJ);
   }
-  const int grid_slots = (int)cursor;
-  // CTA tier: one launch per lanes-per-vertex class (the kernel is specialised on it)
-  struct CtaClass {
-    std::vector<int4> tasks;
-    int threads = 32, size_max = 1;
-  };
-  CtaClass cta_class[4];  // L = 1, 2, 4, 8
+  L_.grid_slots = (int)cursor;
   for (int a : cta_aggs) {
     const int s = size_of(a);
     agg_base[a] = (int)cursor;
@@ -316,14 +319,14 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
       }
     }
   }
-  const int single_begin = (int)cursor;
-  int n_single = 0;
+  L_.single_begin = (int)cursor;
   if (!forces_only) {
     for (int a : by_size[1]) agg_base[a] = (int)cursor++;
-    n_single = (int)by_size[1].size();
+    L_.n_single = (int)by_size[1].size();
   }
-  const int nslots = (int)cursor;
-  const int64_t ld = round_up(std::max(nslots, 1), kTileJ);
+  L_.nslots = (int)cursor;
+  const int64_t ld = round_up(std::max(L_.nslots, 1), kTileJ);
+  L_.ld = ld;
   std::vector<int> vtx((size_t)ld, -1), slot_of(std::max(n, 1), -1), agg_of_slot((size_t)ld, -1);
   for (int a = agg_begin; a < agg_end; ++a) {
     const int s = size_of(a);
@@ -335,9 +338,65 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     }
   }
 
+  // the vertex -> aggregate map: the caller's, or derived from P_T
+  std::vector<int32_t> vA_local;
+  if (v_A == nullptr) {
+    vA_local.assign(std::max(n, 1), 0);
+    for (int a = 0; a < m; ++a)
+      for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) vA_local[P.indices[c]] = a;
+    v_A = vA_local.data();
+  }
+  L_.d_vA.alloc(ctx, std::max(n, 1));
+  L_.d_vtx.alloc(ctx, (size_t)ld);
+  L_.d_slot_of.alloc(ctx, std::max(n, 1));
+  L_.d_agg_base.alloc(ctx, std::max(m, 1));
+  L_.d_agg_of_slot.alloc(ctx, (size_t)ld);
+  L_.d_vA.upload(ctx, v_A, n);
+  L_.d_vtx.upload(ctx, vtx.data(), (size_t)ld);
+  L_.d_slot_of.upload(ctx, slot_of.data(), n);
+  L_.d_agg_base.upload(ctx, agg_base.data(), m);
+  L_.d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
+  // (copies from pageable memory have left the host arrays when cudaMemcpyAsync returns)
+}
+
+template <typename T>
+void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
+                  const double* coords_A, const double* r_A, const double* init,
+                  double* coords_out, int dim, const ge_params& p, bool forces_only,
+                  double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
+  constexpr int NM = Real<T>::kMassArrays;
+  const int n = A.rows, m = P.rows;
+  const int nnz = A.indptr[n];
+  const bool weighted = p.use_weights && A.data != nullptr;
+
+  const bool verbose = std::getenv("GE_VERBOSE") != nullptr;
+  double t_mark = now_ms();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double t = now_ms();
+    std::fprintf(stderr, "[ge] level n=%d %-18s %8.3f ms\n", n, what, t - t_mark);
+    t_mark = t;
+  };
+  // ---- slot layout (host + its device copies): prepared ahead of time or built here ----------
+  LevelLayout own_layout;
+  const LevelLayout* lay = (pre != nullptr && pre->layout != nullptr) ? pre->layout : nullptr;
+  if (lay == nullptr) {
+    build_level_layout(ctx, P, n, v_A, forces_only, agg_begin, agg_end, own_layout);
+    lay = &own_layout;
+  }
+  if (pairs_out) *pairs_out = lay->pairs;
+  const std::vector<int4>& segs = lay->segs;
+  const std::vector<int4>& packs = lay->packs;
+  const CtaClass* cta_class = lay->cta_class;
+  const int grid_slots = lay->grid_slots, single_begin = lay->single_begin, n_single = lay->n_single;
+  const int nslots = lay->nslots;
+  const int64_t ld = lay->ld;
+  const DevBuf<int>&d_vA = lay->d_vA, &d_vtx = lay->d_vtx, &d_slot_of = lay->d_slot_of,
+                   &d_agg_base = lay->d_agg_base, &d_agg_of_slot = lay->d_agg_of_slot;
   lap("host layout");
   // ---- upload ------------------------------------------------------------------------------
-  DevBuf<int> d_I, d_J, d_vA(ctx, std::max(n, 1)), d_vtx(ctx, (size_t)ld), d_slot_of(ctx, std::max(n, 1)), d_agg_base(ctx, std::max(m, 1)), d_agg_of_slot(ctx, (size_t)ld), d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
+  DevBuf<int> d_I, d_J, d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
   DevBuf<double> d_Dw, d_cA(ctx, (size_t)std::max(m, 1) * dim), d_rA(ctx, std::max(m, 1)), d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
   DevBuf<T> d_mass(ctx, (size_t)NM * ld), d_E(ctx, (size_t)dim * ld), d_ew;
   const int* dI;
@@ -362,11 +421,6 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     dJ = d_J.get();
   }
   if (weighted) d_ew.alloc(ctx, std::max(nnz, 1));
-  d_vA.upload(ctx, v_A, n);
-  d_vtx.upload(ctx, vtx.data(), (size_t)ld);
-  d_slot_of.upload(ctx, slot_of.data(), n);
-  d_agg_base.upload(ctx, agg_base.data(), m);
-  d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
   d_cA.upload(ctx, coords_A, (size_t)m * dim);
   d_rA.upload(ctx, r_A, m);
   if (init != nullptr) {
@@ -456,7 +510,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   // ---- CTA tier ----------------------------------------------------------------------------
   std::vector<DevBuf<int4>> d_cta_tasks(4);
   for (int li = 0; li < 4; ++li) {
-    CtaClass& cc = cta_class[li];
+    const CtaClass& cc = cta_class[li];
     if (cc.tasks.empty()) continue;
     d_cta_tasks[li].alloc(ctx, cc.tasks.size());
     d_cta_tasks[li].upload(ctx, cc.tasks.data(), cc.tasks.size());
@@ -529,6 +583,13 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 }
 
 }  // namespace
+
+LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n) {
+  std::unique_ptr<LevelLayout> L(new LevelLayout);
+  build_level_layout(ctx, P_T, n, nullptr, false, 0, P_T.rows, *L);
+  return L.release();
+}
+void free_level_layout(LevelLayout* layout) { delete layout; }
 
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
