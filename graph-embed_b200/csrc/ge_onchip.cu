@@ -704,7 +704,6 @@ const void* cluster_kernel(int L) {
     case 2: return (const void*)k_onchip_cluster<T, D, 2, GA>;
     case 4: return (const void*)k_onchip_cluster<T, D, 4, GA>;
     case 16: return (const void*)k_onchip_cluster<T, D, 16, GA>;
-    case 32: return (const void*)k_onchip_cluster<T, D, 32, GA>;
     default: return (const void*)k_onchip_cluster<T, D, 8, GA>;
   }
 }
@@ -721,7 +720,10 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   int L = 1;
   while (L < 8 && per_cta * (L * 2) <= 512) L *= 2;
   if (L == 8 && per_cta * 16 <= 128) L = 16;
-  if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::min(32, std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("GE_ONCHIP_LANES")) {
+    L = 1;
+    while (L < 16 && L * 2 <= std::atoi(v)) L *= 2;  // 1, 2, 4, 8 or 16
+  }
   while (L > 1 && per_cta * L > 512) L /= 2;
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
   GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");

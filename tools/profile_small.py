@@ -39,7 +39,7 @@ elif mode == "k3sweep":
         x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
         shapes = ((1, 4), (1, 8), (2, 8), (4, 8), (8, 8), (4, 4), (8, 4))
         if os.environ.get("K3_WIDE"):
-            shapes = ((8, 8), (8, 16), (8, 32), (4, 16), (4, 32))
+            shapes = ((8, 8), (8, 16), (4, 16))
         for cs, L in shapes:
             if (n + cs - 1) // cs * L > (1024 if cs == 1 else 512):
                 continue
