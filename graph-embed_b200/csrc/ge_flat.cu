@@ -350,10 +350,7 @@ template <typename T, int D, int G, bool GA, int CAP, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArgs<T> a, const int nchunks) {
   constexpr int kStepCap = CAP;
   constexpr int RPC = 256 / G;
-#ifndef GE_STEP_EU1
-#define GE_STEP_EU1 4
-#endif
-  constexpr int EU = G == 1 ? GE_STEP_EU1 : (G <= 2 ? 4 : 2);
+  constexpr int EU = G <= 2 ? 4 : 2;  // entries in flight per lane (5 or 6 with one lane per row: no gain)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* Ws = reinterpret_cast<T*>(smem_raw);
   int* Js = reinterpret_cast<int*>(smem_raw + 2 * kStepCap * sizeof(T));
