@@ -29,7 +29,32 @@ def pack_levels(As, Ps):
     return d
 
 
+def mint_galerkin():
+    """galerkin_grid30.npz: `P.Mult(A).Mult(P.Transpose())` (examples/embedder.cpp:215) of every level of
+    the grid-30 hierarchy (aggregation from the reference's own partitioner), evaluated by the
+    compiled reference driver with the stand-in linalgcpp container; plus one real-weight level."""
+    O.build(ref=True)
+    assert O.ref_available("strict"), "oracle/_ref missing (needs /root/reference)"
+    A = G.grid2d(30, 30)
+    Ps = O.ref_partition(A, 0.25, matching_iterations=2, nthreads=1)
+    out = {"L": np.int32(len(Ps))}
+    cur = G.canonical(A)
+    for l, P in enumerate(Ps):
+        out["P%d_indptr" % l], out["P%d_indices" % l] = P.indptr, P.indices
+        C = O.ref_galerkin(cur, P)
+        out["C%d_indptr" % l], out["C%d_indices" % l], out["C%d_data" % l] = C.indptr, C.indices, C.data
+        cur = C
+    B = G.canonical(A).copy()
+    B.data = np.random.default_rng(4).uniform(0.5, 2.0, B.nnz)
+    C = O.ref_galerkin(B, Ps[0])
+    out["B_data"], out["CB_indptr"], out["CB_indices"], out["CB_data"] = B.data, C.indptr, C.indices, C.data
+    np.savez_compressed(os.path.join(HERE, "galerkin_grid30.npz"), **out)
+    print("wrote galerkin_grid30.npz")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "galerkin":
+        return mint_galerkin()
     O.build(ref=True)
     assert O.ref_available("strict"), "oracle/_ref missing (needs /root/reference)"
     # ---- flat kernel: positions after k iterations from fixed initial coordinates ---------------

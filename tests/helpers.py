@@ -63,3 +63,17 @@ def layout_stats(A, x):
     extent = np.linalg.norm(x - x.mean(0), axis=1).max()
     return dict(edge_mean=el.mean() / extent, edge_cv=el.std() / el.mean(),
                 pair_mean=dist.mean() / extent)
+
+
+def load_galerkin_golden(graphs):
+    """Galerkin products of the grid-30 hierarchy minted from the compiled reference driver."""
+    z = np.load(os.path.join(GOLDEN, "galerkin_grid30.npz"))
+    A = graphs.canonical(graphs.grid2d(30, 30))
+    Ps, Cs, n = [], [], A.shape[0]
+    for l in range(int(z["L"])):
+        ptr, idx = z["P%d_indptr" % l], z["P%d_indices" % l]
+        m = len(ptr) - 1
+        Ps.append(sp.csr_matrix((np.ones(len(idx)), idx, ptr), shape=(m, n)))
+        Cs.append(sp.csr_matrix((z["C%d_data" % l], z["C%d_indices" % l], z["C%d_indptr" % l]), shape=(m, m)))
+        n = m
+    return A, Ps, Cs, z

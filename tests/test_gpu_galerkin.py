@@ -123,3 +123,19 @@ def test_long_runs_keep_the_sequential_summation_order(ctx, oracle, graphs, n):
     C, st = ctx.galerkin(A, P, with_stats=True)
     assert (st["segments_global"] > 0) == (n > 2500)
     _same(C, oracle.galerkin(A, P))
+
+
+def test_golden_products_of_the_reference_driver(ctx, graphs):
+    """ge_galerkin against tests/golden/galerkin_grid30.npz (the caller's expression run through the
+    compiled reference driver): exact on the unit-weight chain, rounding on the real-weight level."""
+    from helpers import load_galerkin_golden
+    A, Ps, Cs, z = load_galerkin_golden(graphs)
+    cur = A
+    for P, C in zip(Ps, Cs):
+        _same(ctx.galerkin(cur, P), C)
+        cur = C
+    B = A.copy()
+    B.data = z["B_data"]
+    got = ctx.galerkin(B, Ps[0])
+    assert np.array_equal(got.indptr, z["CB_indptr"]) and np.array_equal(got.indices, z["CB_indices"])
+    assert np.abs(got.data - z["CB_data"]).max() < 1e-12

@@ -113,3 +113,22 @@ def test_galerkin_oracle_matches_scipy_product(oracle, graphs):
     C = oracle.galerkin(B, Ps[0])
     R = graphs.galerkin(B, Ps[0])
     assert np.array_equal(C.indices, R.indices) and np.abs(C.data - R.data).max() < 1e-12
+
+
+def test_galerkin_golden(oracle, graphs):
+    """oracle_galerkin reproduces the committed products of `P.Mult(A).Mult(P.Transpose())`
+    (examples/embedder.cpp:215, minted from the compiled reference driver) level by level, bit for
+    bit on the unit-weight chain; the real-weight level to rounding (different association)."""
+    from helpers import load_galerkin_golden
+    A, Ps, Cs, z = load_galerkin_golden(graphs)
+    cur = A
+    for P, C in zip(Ps, Cs):
+        got = oracle.galerkin(cur, P)
+        assert np.array_equal(got.indptr, C.indptr) and np.array_equal(got.indices, C.indices)
+        assert np.array_equal(got.data, C.data)
+        cur = C
+    B = A.copy()
+    B.data = z["B_data"]
+    got = oracle.galerkin(B, Ps[0])
+    assert np.array_equal(got.indptr, z["CB_indptr"]) and np.array_equal(got.indices, z["CB_indices"])
+    assert np.abs(got.data - z["CB_data"]).max() < 1e-12
