@@ -215,3 +215,63 @@ def test_two_rank_symmetric_pair_sums(tmp_path):
     full = (d * (s * c[None, :])[..., None]).sum(1)
     got = np.load(out)
     assert np.abs(got[:n] - full[:n]).max() < 1e-9 * np.abs(full[:n]).max()
+
+
+def _attract_gravity_rows(A, x, c, r0, r1, attract=1.0, gravity=1.0):
+    """include/forceatlas.hpp:169-211 for rows [r0, r1) with the default options: attraction
+    (xj - xi) * attract * a_ij and gravity -x/|x| * gravity * (deg + 1)."""
+    F = np.zeros((r1 - r0, x.shape[1]))
+    for i in range(r0, r1):
+        for e in range(A.indptr[i], A.indptr[i + 1]):
+            j = A.indices[e]
+            F[i - r0] += (x[j] - x[i]) * (attract * A.data[e])
+        F[i - r0] -= x[i] / np.sqrt((x[i] * x[i]).sum()) * (gravity * c[i])
+    return F
+
+
+def _sym_iteration_worker(rank, world, port, iters, out):
+    """The symmetric multi-rank iteration end to end with numpy standing in for the kernels:
+    pair shares -> exchange of the pair sums -> attraction/gravity/step on the own row block ->
+    in-place all-gather of the coordinates."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest  # noqa: F401
+    from graph_embed_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A, z = load_flat_golden()
+    n, dim = A.shape[0], 2
+    r0, r1, R, ld = sharding.row_block(n, world, rank)
+    c = np.zeros(ld)
+    c[:n] = np.asarray(A.sum(axis=1)).ravel() + 1.0
+    cur = torch.zeros(dim, ld, dtype=torch.float64)
+    cur[:, :n] = torch.from_numpy(z["x0_d2"].T.copy())
+    nxt = cur.clone()
+    fprev = np.zeros((r1 - r0, dim))
+    share = sharding.pair_share(ld, world, rank, rows_per_block=64, tile=16)  # several units at n = 144
+    for _ in range(iters):
+        x = np.ascontiguousarray(cur.numpy().T)                      # [ld, dim]
+        S = _pair_sums_share(x, c, share, tile=16)
+        sums = torch.from_numpy(np.ascontiguousarray(S.T))
+        sharding.reduce_scatter_pair_sums(dist, sums, rank, R)
+        F = sums[:, r0:r1].numpy().T * c[r0:r1, None] * 1.0          # * c_i * repel
+        F = F + _attract_gravity_rows(A, x[:n], c, r0, r1)
+        nxt[:, r0:r1] = torch.from_numpy(_step_rows(x[r0:r1], F, fprev).T.copy())
+        fprev = F.copy()
+        sharding.allgather_coords(dist, nxt, rank, R)
+        cur, nxt = nxt, cur
+    if rank == 0:
+        np.save(out, cur[:, :n].numpy().T)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_symmetric_iterations_follow_the_reference(tmp_path, oracle):
+    """Two iterations of the symmetric two-rank scheme land on the compiled reference's golden
+    positions up to summation order (unordered pairs, partial sums per rank)."""
+    iters = 2
+    out = str(tmp_path / "sym_coords.npy")
+    mp.spawn(_sym_iteration_worker, args=(2, _free_port(), iters, out), nprocs=2, join=True)
+    _, z = load_flat_golden()
+    ref = z["x_d2_k%d" % iters]
+    assert np.abs(np.load(out) - ref).max() < 1e-9 * np.abs(ref).max()
