@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <random>
 #include <atomic>
@@ -169,6 +170,7 @@ struct HeapItem {
 void grow_balls(std::vector<Event>& ev, double* r_A, int m, const int* local, int nloc,
                 std::vector<int>& inc_ptr, std::vector<int>& inc, std::vector<int>& ver,
                 std::vector<HeapItem>& heap) {
+  static thread_local std::vector<int> fill;  // scratch: families are many and small
   const int E = (int)ev.size();
   inc_ptr.assign(nloc + 1, 0);
   for (const Event& e : ev) {
@@ -178,7 +180,7 @@ void grow_balls(std::vector<Event>& ev, double* r_A, int m, const int* local, in
   for (int v = 0; v < nloc; ++v) inc_ptr[v + 1] += inc_ptr[v];
   inc.resize(2 * (size_t)E);
   {
-    std::vector<int> fill(inc_ptr.begin(), inc_ptr.end() - 1);
+    fill.assign(inc_ptr.begin(), inc_ptr.end() - 1);
     for (int x = 0; x < E; ++x) {
       inc[fill[local[ev[x].i]]++] = x;
       inc[fill[local[ev[x].j]]++] = x;
@@ -245,15 +247,40 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
   const int mc = P_T_c->rows;
   const int32_t* PI = P_T_c->indptr;
   const int32_t* PJ = P_T_c->indices;
+  // a few host threads pull blocks of families off a counter (every loop below touches only the
+  // members of its own families, so the results do not depend on the schedule)
+  const int kBlock = 512;
+  const int nthreads = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u,
+                                                   (unsigned)((mc + kBlock - 1) / kBlock)}));
+  auto for_family_blocks = [&](const std::function<void(int, int)>& body) {
+    if (nthreads <= 1) {
+      body(0, mc);
+      return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&] {
+        for (;;) {
+          const int b0 = next.fetch_add(kBlock);
+          if (b0 >= mc) break;
+          body(b0, std::min(mc, b0 + kBlock));
+        }
+      });
+    for (auto& th : pool) th.join();
+  };
   std::vector<int> parent(m, -1);  // :684
-  for (int b = 0; b < mc; ++b)
-    for (int c = PI[b]; c < PI[b + 1]; ++c) parent[PJ[c]] = b;
+  for_family_blocks([&](int b0, int b1) {
+    for (int b = b0; b < b1; ++b)
+      for (int c = PI[b]; c < PI[b + 1]; ++c) parent[PJ[c]] = b;
+  });
   // :686-756: the families are independent (the reference runs this loop under `omp parallel
-  // for`, src/embed.cpp:685); here a few host threads pull blocks of families off a counter.
-  auto families = [&](int b0, int b1, std::vector<int>& loc) {
-    std::vector<Event> ev;
-    std::vector<int> ip, in, vr;
-    std::vector<HeapItem> hp;
+  // for`, src/embed.cpp:685).
+  auto families = [&](int b0, int b1) {
+    static thread_local std::vector<Event> ev;
+    static thread_local std::vector<int> ip, in, vr, loc;
+    static thread_local std::vector<HeapItem> hp;
+    if ((int)loc.size() < m) loc.resize(m);
     for (int b = b0; b < b1; ++b) {
       const int s = PI[b + 1] - PI[b];
       if (s == 1) {
@@ -273,41 +300,25 @@ void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_
       grow_balls(ev, r_A, m, loc.data(), s, ip, in, vr, hp);
     }
   };
-  const int kBlock = 512;
-  const int nthreads = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u,
-                                                   (unsigned)((mc + kBlock - 1) / kBlock)}));
-  if (nthreads <= 1) {
-    families(0, mc, local);
-  } else {
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; ++t)
-      pool.emplace_back([&] {
-        std::vector<int> loc(std::max(m, 1));
-        for (;;) {
-          const int b0 = next.fetch_add(kBlock);
-          if (b0 >= mc) break;
-          families(b0, std::min(mc, b0 + kBlock), loc);
-        }
-      });
-    for (auto& th : pool) th.join();
-  }
-  for (int b = 0; b < mc; ++b) {  // :757-777 shrink each family into its parent ball
-    const double* cb = coords_Ac + (size_t)b * dim;
-    double alpha = 0.0;
-    for (int c = PI[b]; c < PI[b + 1]; ++c) {
-      const int a = PJ[c];
-      alpha = std::max(alpha, dist(cb, coords_A + (size_t)a * dim, dim) + r_A[a]);
+  for_family_blocks(families);
+  for_family_blocks([&](int b0, int b1) {  // :757-777 shrink each family into its parent ball
+    for (int b = b0; b < b1; ++b) {
+      const double* cb = coords_Ac + (size_t)b * dim;
+      double alpha = 0.0;
+      for (int c = PI[b]; c < PI[b + 1]; ++c) {
+        const int a = PJ[c];
+        alpha = std::max(alpha, dist(cb, coords_A + (size_t)a * dim, dim) + r_A[a]);
+      }
+      if (alpha < 0.000001) alpha = 0.000001;
+      const double scale = r_Ac[b] / alpha;
+      for (int c = PI[b]; c < PI[b + 1]; ++c) {
+        const int a = PJ[c];
+        for (int k = 0; k < dim; ++k)
+          coords_A[(size_t)a * dim + k] = cb[k] + scale * (coords_A[(size_t)a * dim + k] - cb[k]);
+        r_A[a] = scale * r_A[a];
+      }
     }
-    if (alpha < 0.000001) alpha = 0.000001;
-    const double scale = r_Ac[b] / alpha;
-    for (int c = PI[b]; c < PI[b + 1]; ++c) {
-      const int a = PJ[c];
-      for (int k = 0; k < dim; ++k)
-        coords_A[(size_t)a * dim + k] = cb[k] + scale * (coords_A[(size_t)a * dim + k] - cb[k]);
-      r_A[a] = scale * r_A[a];
-    }
-  }
+  });
 }
 
 namespace {
