@@ -778,7 +778,7 @@ void launch_staged_g(ge_context* ctx, const StepArgs<T>& a) {
 }
 template <typename T, int D, bool GA>
 void launch_staged_d(ge_context* ctx, const StepArgs<T>& a, int group) {
-  // (a 3072-entry / 3-CTA shape of the one-lane variant spills at 85 registers: 47 % vs 58 %)
+  // (a 3072-entry / 3-CTA shape of the one-lane variant measured 47 % vs 58 %; cause not isolated)
   if (group <= 1) launch_staged_c<T, D, 1, GA, 4096, 2>(ctx, a);
   else if (group <= 2) launch_staged_g<T, D, 2, GA>(ctx, a);
   else if (group <= 4) launch_staged_g<T, D, 4, GA>(ctx, a);
