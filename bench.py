@@ -131,6 +131,19 @@ def cpu_flat_rate(O, dim, n_sample, iters, threads, kind):
     return float(n) * (n - 1) * iters / dt, dt, n
 
 
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on.  torchrun exports
+    OMP_NUM_THREADS=1 into its workers, so omp_get_max_threads() is not the box's core count
+    there; the affinity mask is."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+REF_ITERS_PER_STEP = 2  # the same sample shape in --impl reference and in cpu_baseline
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,25 +151,28 @@ def run_reference(args):
     entry.load_package()
     O = entry.load_oracle()
     kind = "reference" if O.ref_available("fast") else "port"
-    threads = O.ref_lib("fast").ref_max_threads() if kind == "reference" else 1
+    threads = host_threads() if kind == "reference" else 1
     n_sample = args.ref_n
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):
         cpu_flat_rate(O, args.dim, n_sample, 1, threads, kind)
     t_total, pairs_total, n_eff = 0.0, 0.0, 0
     for _ in range(args.steps):
-        rate, dt, n_eff = cpu_flat_rate(O, args.dim, n_sample, 1, threads, kind)
+        rate, dt, n_eff = cpu_flat_rate(O, args.dim, n_sample, REF_ITERS_PER_STEP, threads, kind)
         t_total += dt
         pairs_total += rate * dt
     value = pairs_total / t_total
-    sample = ("flat forceAtlas, 1 iteration per step on a %d-vertex RGG (avg degree 10) from the "
-              "same generator as the %d-vertex workload; pair-interactions/s is size-independent "
-              "for the O(n^2) kernel" % (n_eff, args.n))
+    sample = ("flat forceAtlas, %d iterations per step on a %d-vertex RGG (avg degree 10) from the "
+              "same generator as the %d-vertex workload (a direct run is ~100 s per iteration); "
+              "pair-interactions/s is size-independent for the O(n^2) kernel, so the rate is "
+              "quoted for the workload's n" % (REF_ITERS_PER_STEP, n_eff, args.n))
     line = {"impl": "reference", "metric": "forceatlas_pair_interactions_per_sec", "value": value,
             "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "iters_per_sec_at_workload_n": value / (float(args.n) * (args.n - 1)),
-            "config": workload_config(args),
+            "config": dict(workload_config(args), reference_sample_n=n_eff,
+                           reference_iterations_per_step=REF_ITERS_PER_STEP,
+                           reference_threads=threads),
             "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": threads,
                              "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0,
@@ -318,6 +334,11 @@ def run_ours(args):
                "config": workload_config(args), "gpu_launches": launches, "clocks": clocks,
                "roofline": roof, "roofline_attraction": roof2}
 
+    # ---- parity at this N (outside the timed region) ---------------------------------------------
+    parity = bench_parity(args, torch, dist, capi, ctx, plan, A, x0, params, world, rank, r0, r1, one_step, barrier, dev)
+    if rank == 0:
+        out.update(parity)
+
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------
     e2e = bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier, one_step)
     if rank == 0:
@@ -339,6 +360,70 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity["parity_max_err"] > PARITY_TOL or not parity["parity_ok"]:
+        log("[bench] PARITY FAILURE: %r" % (parity,))
+        sys.exit(3)
+
+
+PARITY_TOL = 1e-10  # FP64 forces, relative to the vertex's conditioning scale (tests/helpers.py)
+
+
+def bench_parity(args, torch, dist, capi, ctx, plan, A, x0, params, world, rank, r0, r1, one_step, barrier, dev):
+    """One more step from the known state x0, checked on every rank: the forces of sampled owned
+    rows against the CPU oracle (include/forceatlas.hpp:148-212 restated, oracle/ -- the checker,
+    never the thing measured), the positions of those rows against the oracle's forces pushed
+    through the step formula (:244-261), and at N > 1 every position against a single-GPU plan of
+    the same graph on rank 0.  The errors are max-reduced over the ranks."""
+    O = entry.load_oracle()
+    n, dim = A.shape[0], args.dim
+    plan.upload(x0)
+    barrier()
+    one_step()
+    barrier()
+    F = plan.download_forces()   # owned rows, forces of the step just taken
+    x1 = plan.download()         # all rows (gathered)
+    per_rank = max(4, 32 // world)
+    rng = np.random.default_rng(1234 + rank)
+    rows = np.sort(rng.choice(np.arange(r0, r1), size=min(per_rank, r1 - r0), replace=False))
+    ferr = xerr = 0.0
+    p = O.Params()
+    for r in rows:
+        Fr, S = O.flat_forces(A, dim, x0, p, rows=(int(r), int(r) + 1))
+        f, sc = Fr[r], max(S[r], 1e-300)
+        ferr = max(ferr, float(np.linalg.norm(F[r - r0] - f) / sc))
+        # step (:244-261) from zero previous forces: swing = |f|, speed = ks / (1 + sqrt(swing)),
+        # capped at ksmax / |f|
+        fn = float(np.sqrt((f * f).sum()))
+        speed = p.ks * p.tolerate / (1.0 + p.tolerate * np.sqrt(fn))
+        if fn > 0:
+            speed = min(speed, p.ksmax / fn)
+        xr = x0[r] + f * speed
+        # a force error of 1e-10*scale moves the vertex by at most speed * that
+        xerr = max(xerr, float(np.linalg.norm(x1[r] - xr) / max(speed * sc, 1e-300)))
+    t = torch.tensor([ferr, xerr], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ferr, xerr = float(t[0].item()), float(t[1].item())
+    out = {"parity_max_err": max(ferr, xerr), "parity_force_err": ferr, "parity_position_err": xerr,
+           "parity_rows_checked": int(per_rank * world), "parity_tolerance": PARITY_TOL,
+           "parity_vs_single_gpu_plan": None, "parity_ok": True}
+    if world > 1:
+        ok = 1.0
+        if rank == 0:  # the same step on ONE GPU: positions of every vertex
+            single = ctx.flat_plan(A, dim, params)
+            single.upload(x0)
+            single.iterate(1)
+            xs = single.download()
+            single.close()
+            extent = float(np.abs(xs).max())
+            d = float(np.abs(x1 - xs).max() / extent)
+            out["parity_vs_single_gpu_plan"] = d
+            ok = 1.0 if d < 1e-9 else 0.0
+        t = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        out["parity_ok"] = bool(t.item() > 0.5)
+    log("[bench] parity: %r" % (out,))
+    return out
 
 
 def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, R, ptr_to_buf, ld, alg, barrier, one_step):
@@ -505,7 +590,7 @@ def bench_embed(args, capi, ctx, graphs):
     if not args.no_cpu:
         O = entry.load_oracle()
         if O.ref_available("fast"):
-            threads = O.ref_lib("fast").ref_max_threads()
+            threads = host_threads()
             best = None
             for nt in sorted({1, threads}):
                 with stdout_to_stderr():
@@ -521,14 +606,19 @@ def bench_cpu_baseline(args):
     sample of the same workload, ~10-30 s of CPU work."""
     O = entry.load_oracle()
     kind = "reference" if O.ref_available("fast") else "port"
-    threads = O.ref_lib("fast").ref_max_threads() if kind == "reference" else 1
-    rate, dt, n = cpu_flat_rate(O, args.dim, 6000, 1, threads, kind)      # calibrate
-    n_sample = int(min(60000, max(8000, (rate * 15.0 / 2) ** 0.5)))        # ~15 s for 2 iterations
-    rate, dt, n = cpu_flat_rate(O, args.dim, n_sample, 2, threads, kind)
-    return {"value": rate, "unit": "pair-interactions/s", "cores": threads, "kind": kind,
-            "seconds": dt,
-            "sample": "flat forceAtlas, 2 iterations on a %d-vertex RGG (avg degree 10) of the same "
-                      "generator; the O(n^2) kernel's pair rate is size-independent" % n}
+    threads = host_threads() if kind == "reference" else 1
+    cpu_flat_rate(O, args.dim, 6000, 1, threads, kind)      # warm the thread pool / page in the library
+    # the same sample as `--impl reference` (args.ref_n vertices, 2 iterations per step, 2 steps)
+    t_total, pairs_total, n = 0.0, 0.0, 0
+    for _ in range(2):
+        rate, dt, n = cpu_flat_rate(O, args.dim, args.ref_n, REF_ITERS_PER_STEP, threads, kind)
+        t_total += dt
+        pairs_total += rate * dt
+    return {"value": pairs_total / t_total, "unit": "pair-interactions/s", "cores": threads, "kind": kind,
+            "seconds": t_total,
+            "sample": "flat forceAtlas, 2 steps of %d iterations on a %d-vertex RGG (avg degree 10) of the "
+                      "same generator (the --impl reference sample); the O(n^2) kernel's pair rate is "
+                      "size-independent" % (REF_ITERS_PER_STEP, n)}
 
 
 def main():

@@ -50,7 +50,8 @@ class EmbedStats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("coarse_ms", C.c_double), ("levels_ms", C.c_double),
                 ("host_radii_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("pair_interactions", C.c_double), ("edge_visits", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("grid_tier_ms", C.c_double),
+                ("device_radii_ms", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -781,6 +781,8 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     else ge_embed_options_default(&run.opt);
     const int64_t launches0 = ctx->launches;
     const double h0 = ctx->h2d_bytes, d0 = ctx->d2h_bytes;
+    ctx->grid_tier_ms = 0;
+    ctx->radii_ms = 0;
     const double t0 = now_ms();
     std::vector<double> r_A, coords_A;
     run.final_out = n_levels > 0 ? coords_out : nullptr;
@@ -794,6 +796,8 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     run.st.kernel_launches = ctx->launches - launches0;
     run.st.h2d_bytes = ctx->h2d_bytes - h0;
     run.st.d2h_bytes = ctx->d2h_bytes - d0;
+    run.st.grid_tier_ms = ctx->grid_tier_ms;
+    run.st.device_radii_ms = ctx->radii_ms;
     if (stats) *stats = run.st;
   });
 }

@@ -28,6 +28,10 @@ struct ge_context {
   bool own_stream = false;
   int64_t launches = 0;
   double h2d_bytes = 0, d2h_bytes = 0;
+  // device time of the large-aggregate (multi-CTA) tier of the per-aggregate solver, accumulated
+  // over the levels of one ge_embed call (CUDA events on the context stream)
+  double grid_tier_ms = 0;
+  double radii_ms = 0;  // device time of the ball-radius / rescale kernels
 };
 
 namespace ge {

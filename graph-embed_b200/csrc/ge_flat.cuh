@@ -77,6 +77,16 @@ struct SymBlockDesc {
   long long col_off;  // element offset of the slab, laid out [D][ncols]
 };
 
+// Where the rows of one 256-entry tile get their sums from (k_sym_reduce): the plan block that
+// sweeps them (row side; -1: none in this plan), and the plan blocks of the same segment that lie
+// above them and therefore pushed on them from the column side.
+struct SymTileRef {
+  int row_block;  // index into the plan's block list, or -1
+  int col_b0;     // first plan block of the same segment
+  int col_n;      // number of plan blocks of that segment strictly above this tile's block
+  int pad;
+};
+
 template <typename T>
 struct RepSymArgs {
   const T* pos;      // [D][ld]
@@ -85,32 +95,43 @@ struct RepSymArgs {
   T* partial;        // [grid][2][D][rows_per_block] row sums of blocks shared between CTAs
   T* colpartial;     // column-side sums, one slab per block (written exactly once per launch)
   const SymBlockDesc* blocks;
+  const SymTileRef* tiles;  // [ld / kTileJ]
   int64_t ld;
   long long total_units;
   int nblocks, rows_per_block;
-  int gb0;           // global index (row0 / rows_per_block) of blocks[0]
   T eps2;
+  T out_scale;       // != 0: S = sums * c_i * out_scale (the force itself); 0: raw sums
 };
 
-// Launch plan of the symmetric sweep over rows/columns [0, ld): share `part` of `parts` equal
-// contiguous cuts of the triangular unit list (parts > 1: every rank produces partial sums over
-// the full length, which the ranks add with a reduce-scatter).
+struct SymSegment {  // rows == columns [row0, row1); row0 a multiple of kTileJ
+  int row0, row1;
+};
+
+// Launch plan of the symmetric sweep over a set of disjoint segments (flat solve: one segment
+// [0, ld); multilevel: one segment per large aggregate, all pairs inside each): share `part` of
+// `parts` equal contiguous cuts of the triangular unit list (parts > 1: every rank produces partial
+// sums over the full length, which the ranks add with a reduce-scatter).
 template <typename T>
 class RepulsionSymPlan {
  public:
   RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int part, int parts);
+  RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, const std::vector<SymSegment>& segments);
   // bytes of column-side scratch the plan would need (worst share)
   static double scratch_bytes(int dim, int64_t ld, int parts);
   // S[k][i] = sum over this plan's pairs; multiply by c_i * repel to obtain the force
-  void launch(const T* pos, const T* mass, T* S, T eps2);
+  // (out_scale != 0: the kernel does it, S = sums * c_i * out_scale)
+  void launch(const T* pos, const T* mass, T* S, T eps2, T out_scale = (T)0);
   long long pairs() const { return pairs_; }  // ordered pairs covered by one launch
+  int grid() const { return grid_; }
 
  private:
+  void init(const std::vector<SymSegment>& segments, int part, int parts);
   ge_context* ctx_;
-  int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0, gb0_ = 0;
-  int64_t ld_ = 0;
+  int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0;
+  int64_t ld_ = 0, reduce_len_ = 0;
   long long total_units_ = 0, pairs_ = 0;
   DevBuf<SymBlockDesc> blocks_;
+  DevBuf<SymTileRef> tiles_;
   DevBuf<T> partial_, colpartial_;
   size_t colpartial_elems_ = 0;
 };

@@ -264,47 +264,57 @@ __global__ void __launch_bounds__(SymShape<IPT>::kThreads) k_repulsion_sym(const
 }
 
 // S_i = (row sums of i, from S itself or from the CTA partial slots in CTA order)
-//       - (column sums of i, one term per earlier block, in block order).
+//       - (column sums of i, one term per block of the same segment above it, in block order).
 template <typename T, int D>
-__global__ void __launch_bounds__(256) k_sym_reduce(const RepSymArgs<T> a, int grid) {
+__global__ void __launch_bounds__(256) k_sym_reduce(const RepSymArgs<T> a, int grid, int64_t len) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.ld) return;
-  const int bi = (int)(i / a.rows_per_block) - a.gb0;
+  if (i >= len) return;
+  const SymTileRef tr = a.tiles[i / kTileJ];
   T acc[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) acc[k] = (T)0;
-  if (bi >= 0 && bi < a.nblocks) {
-    const SymBlockDesc bd = a.blocks[bi];
-    const int r = (int)(i - bd.row0);
-    const long long W = a.total_units, G = grid;
-    const long long U0 = bd.unit0, U1 = bd.unit0 + bd.ntiles;
-    long long c = U0 * G / W;
-    while (c + 1 < G && W * (c + 1) / G <= U0) ++c;
-    while (c > 0 && W * c / G > U0) --c;
-    if (W * c / G <= U0 && W * (c + 1) / G >= U1) {  // swept whole by one CTA
+  bool live = true;
+  if (tr.row_block >= 0) {
+    const SymBlockDesc bd = a.blocks[tr.row_block];
+    live = i < bd.row1;  // padding rows behind the end of a segment
+    if (live) {
+      const int r = (int)(i - bd.row0);
+      const long long W = a.total_units, G = grid;
+      const long long U0 = bd.unit0, U1 = bd.unit0 + bd.ntiles;
+      long long c = U0 * G / W;
+      while (c + 1 < G && W * (c + 1) / G <= U0) ++c;
+      while (c > 0 && W * c / G > U0) --c;
+      if (W * c / G <= U0 && W * (c + 1) / G >= U1) {  // swept whole by one CTA
 #pragma unroll
-      for (int k = 0; k < D; ++k) acc[k] = a.S[(int64_t)k * a.ld + i];
-    } else {
-      for (long long cc = c; cc < G && W * cc / G < U1; ++cc) {
-        const long long v0 = W * cc / G, v1 = W * (cc + 1) / G;
-        if (v1 <= U0 || v0 >= v1) continue;
-        const int slot = (max(v0, U0) == v0) ? 0 : 1;
+        for (int k = 0; k < D; ++k) acc[k] = a.S[(int64_t)k * a.ld + i];
+      } else {
+        for (long long cc = c; cc < G && W * cc / G < U1; ++cc) {
+          const long long v0 = W * cc / G, v1 = W * (cc + 1) / G;
+          if (v1 <= U0 || v0 >= v1) continue;
+          const int slot = (max(v0, U0) == v0) ? 0 : 1;
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-          acc[k] += a.partial[(((size_t)cc * 2 + slot) * D + k) * a.rows_per_block + r];
+          for (int k = 0; k < D; ++k)
+            acc[k] += a.partial[(((size_t)cc * 2 + slot) * D + k) * a.rows_per_block + r];
+        }
       }
     }
   }
-  const int nb = min(a.nblocks, max(bi, 0));
+  if (live) {
 #pragma unroll 4
-  for (int bb = 0; bb < nb; ++bb) {
-    const int c0 = __ldg(&a.blocks[bb].col_t0) * kTileJ;
-    const int nc = __ldg(&a.blocks[bb].ncols);
-    const long long off = __ldg(&a.blocks[bb].col_off);
-    if (i >= c0 && i < (int64_t)c0 + nc) {
+    for (int bb = tr.col_b0; bb < tr.col_b0 + tr.col_n; ++bb) {
+      const int c0 = __ldg(&a.blocks[bb].col_t0) * kTileJ;
+      const int nc = __ldg(&a.blocks[bb].ncols);
+      const long long off = __ldg(&a.blocks[bb].col_off);
+      if (i >= c0 && i < (int64_t)c0 + nc) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) acc[k] -= a.colpartial[off + (int64_t)k * nc + (i - c0)];
+        for (int k = 0; k < D; ++k) acc[k] -= a.colpartial[off + (int64_t)k * nc + (i - c0)];
+      }
     }
+  }
+  if (a.out_scale != (T)0) {
+    const T sc = a.mass[i] * a.out_scale;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] *= sc;
   }
 #pragma unroll
   for (int k = 0; k < D; ++k) a.S[(int64_t)k * a.ld + i] = acc[k];
@@ -332,52 +342,71 @@ size_t sym_smem(int dim, int threads) {
          (size_t)(threads / 32) * dim * kTileJ * sizeof(T) + kRepStages * sizeof(uint64_t);
 }
 
-// The triangular unit list over [0, ld): block g covers rows [g*RB, min(ld,(g+1)*RB)) and the
-// tiles from its own first row to the end.  Returns the blocks clipped to units [U0, U1).
+// The triangular unit list of a set of segments: inside segment [s0, s1), block g covers rows
+// [s0 + g*RB, min(s1, s0 + (g+1)*RB)) and the column tiles from its own first row to the end of the
+// segment.  Returns the blocks clipped to units [U0, U1) of the concatenated list, and for every
+// 256-row tile of [0, ld) where its sums come from.
 struct SymLayout {
   std::vector<SymBlockDesc> blocks;
+  std::vector<SymTileRef> tiles;
   long long units = 0, colpartial_elems = 0, pairs = 0;
-  int gb0 = 0;
+  int64_t reduce_len = 0;
 };
-SymLayout sym_layout(int dim, int64_t ld, int rb, int part, int parts) {
-  const int ntile = (int)(ld / kTileJ);
-  const int nblk = (int)((ld + rb - 1) / rb);
+SymLayout sym_layout(int dim, int64_t ld, const std::vector<SymSegment>& segs, int rb, int part, int parts) {
+  auto seg_tiles = [&](const SymSegment& sg) { return (int)((sg.row1 - (int64_t)sg.row0 + kTileJ - 1) / kTileJ); };
   long long total = 0;
-  for (int g = 0; g < nblk; ++g) total += ntile - (int)((int64_t)g * rb / kTileJ);
+  for (const auto& sg : segs) {
+    const int nt = seg_tiles(sg);
+    const int nblk = (sg.row1 - sg.row0 + rb - 1) / rb;
+    for (int g = 0; g < nblk; ++g) total += nt - (int)((int64_t)g * rb / kTileJ);
+  }
   const long long U0 = total * part / parts, U1 = total * (part + 1) / parts;
   SymLayout L;
+  L.tiles.assign((size_t)(ld / kTileJ), SymTileRef{-1, 0, 0, 0});
   long long prefix = 0;
-  bool first = true;
-  for (int g = 0; g < nblk; ++g) {
-    const int tf = (int)((int64_t)g * rb / kTileJ);
-    const long long b0 = prefix, b1 = prefix + (ntile - tf);
-    prefix = b1;
-    const long long lo = std::max(b0, U0), hi = std::min(b1, U1);
-    if (lo >= hi) continue;
-    SymBlockDesc d;
-    d.row0 = g * rb;
-    d.row1 = (int)std::min<int64_t>(ld, (int64_t)(g + 1) * rb);
-    d.t_first = tf + (int)(lo - b0);
-    d.ntiles = (int)(hi - lo);
-    d.tile_sym0 = (int)((d.row1 + kTileJ - 1) / kTileJ);
-    d.col_t0 = std::max(d.t_first, d.tile_sym0);
-    d.ncols = std::max(0, d.t_first + d.ntiles - d.col_t0) * kTileJ;
-    d.unit0 = L.units;
-    d.col_off = L.colpartial_elems;
-    L.units += d.ntiles;
-    L.colpartial_elems += (long long)dim * d.ncols;
-    const long long rows = d.row1 - d.row0;
-    L.pairs += rows * (long long)(d.col_t0 - d.t_first) * kTileJ + 2 * rows * (long long)d.ncols;
-    if (first) L.gb0 = g;
-    first = false;
-    L.blocks.push_back(d);
+  for (const auto& sg : segs) {
+    const int nt = seg_tiles(sg);
+    const int t_seg = sg.row0 / kTileJ;  // global index of the segment's first tile
+    const int nblk = (sg.row1 - sg.row0 + rb - 1) / rb;
+    const int seg_b0 = (int)L.blocks.size();
+    L.reduce_len = std::max<int64_t>(L.reduce_len, (int64_t)(t_seg + nt) * kTileJ);
+    for (int g = 0; g < nblk; ++g) {
+      const int tf = (int)((int64_t)g * rb / kTileJ);  // first tile of the block, within the segment
+      const long long b0 = prefix, b1 = prefix + (nt - tf);
+      prefix = b1;
+      const int row0 = sg.row0 + g * rb;
+      const int row1 = (int)std::min<int64_t>(sg.row1, (int64_t)row0 + rb);
+      const int bt1 = std::min(nt, tf + rb / kTileJ);  // the block's own row tiles [tf, bt1)
+      const long long lo = std::max(b0, U0), hi = std::min(b1, U1);
+      const int above = (int)L.blocks.size() - seg_b0;  // plan blocks of this segment above block g
+      int self = -1;
+      if (lo < hi) {
+        SymBlockDesc d;
+        d.row0 = row0;
+        d.row1 = row1;
+        d.t_first = t_seg + tf + (int)(lo - b0);
+        d.ntiles = (int)(hi - lo);
+        d.tile_sym0 = t_seg + (int)((row1 - sg.row0 + kTileJ - 1) / kTileJ);
+        d.col_t0 = std::max(d.t_first, d.tile_sym0);
+        d.ncols = std::max(0, d.t_first + d.ntiles - d.col_t0) * kTileJ;
+        d.unit0 = L.units;
+        d.col_off = L.colpartial_elems;
+        L.units += d.ntiles;
+        L.colpartial_elems += (long long)dim * d.ncols;
+        const long long rows = d.row1 - d.row0;
+        L.pairs += rows * (long long)(d.col_t0 - d.t_first) * kTileJ + 2 * rows * (long long)d.ncols;
+        self = (int)L.blocks.size();
+        L.blocks.push_back(d);
+      }
+      for (int t = tf; t < bt1; ++t) L.tiles[(size_t)t_seg + t] = SymTileRef{self, seg_b0, above, 0};
+    }
   }
   return L;
 }
 }  // namespace
 
 void sym_share(int64_t ld, int part, int parts, std::vector<int>& out) {
-  const SymLayout L = sym_layout(2, ld, 1024, part, parts);
+  const SymLayout L = sym_layout(2, ld, {SymSegment{0, (int)ld}}, 1024, part, parts);
   out.clear();
   for (const auto& d : L.blocks) {
     const int v[5] = {d.row0, d.row1, d.t_first, d.ntiles, d.tile_sym0};
@@ -395,6 +424,19 @@ double RepulsionSymPlan<T>::scratch_bytes(int dim, int64_t ld, int parts) {
 template <typename T>
 RepulsionSymPlan<T>::RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int part, int parts)
     : ctx_(ctx), dim_(dim), ld_(ld) {
+  init({SymSegment{0, (int)ld}}, part, parts);
+}
+
+template <typename T>
+RepulsionSymPlan<T>::RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld,
+                                      const std::vector<SymSegment>& segments)
+    : ctx_(ctx), dim_(dim), ld_(ld) {
+  init(segments, 0, 1);
+}
+
+template <typename T>
+void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part, int parts) {
+  ge_context* ctx = ctx_;
   // measured on B200 (tools/sweep_sym.py, n = 300k): FP64 is best with 2 rows per thread and 512
   // threads (d = 2: 53.8 ms vs 54.3; d = 3: 68.6 vs 73.8), FP32 with 4 rows and 256 threads
   // (25.8 vs 27.5; 32.1 vs 38.0); 8-column groups beat 4-column groups everywhere by 5-8 %
@@ -409,28 +451,32 @@ RepulsionSymPlan<T>::RepulsionSymPlan(ge_context* ctx, int dim, int64_t ld, int 
   int occ = 0;
   GE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads_, smem));
   GE_REQUIRE(occ > 0, "symmetric repulsion kernel does not fit on an SM");
-  SymLayout L = sym_layout(dim_, ld_, rb, part, parts);
+  for (const auto& sg : segments)
+    GE_REQUIRE(sg.row0 % kTileJ == 0 && sg.row0 <= sg.row1 && sg.row1 <= ld_, "bad segment");
+  SymLayout L = sym_layout(dim_, ld_, segments, rb, part, parts);
   nblocks_ = (int)L.blocks.size();
   total_units_ = L.units;
   pairs_ = L.pairs;
-  gb0_ = L.gb0;
+  reduce_len_ = parts > 1 ? ld_ : L.reduce_len;  // multi-rank: every row's sums enter the reduce-scatter
   grid_ = (int)std::min<long long>((long long)ctx->sm_count * occ, std::max<long long>(L.units, 1));
   blocks_.alloc(ctx, std::max<size_t>(L.blocks.size(), 1));
   blocks_.upload(ctx, L.blocks.data(), L.blocks.size());
+  tiles_.alloc(ctx, std::max<size_t>(L.tiles.size(), 1));
+  tiles_.upload(ctx, L.tiles.data(), L.tiles.size());
   partial_.alloc(ctx, (size_t)grid_ * 2 * dim_ * rb);
   colpartial_elems_ = (size_t)std::max<long long>(L.colpartial_elems, 1);
   colpartial_.alloc(ctx, colpartial_elems_);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
   if (std::getenv("GE_VERBOSE"))
     std::fprintf(stderr,
-                 "[ge] symmetric repulsion plan: threads=%d ipt=%d cg=%d grid=%d (occ %d) blocks=%d "
-                 "units=%lld column scratch %.1f MB\n",
-                 threads_, ipt_, cg_, grid_, occ, nblocks_, total_units_,
+                 "[ge] symmetric repulsion plan: segments=%zu threads=%d ipt=%d cg=%d grid=%d (occ %d) "
+                 "blocks=%d units=%lld column scratch %.1f MB\n",
+                 segments.size(), threads_, ipt_, cg_, grid_, occ, nblocks_, total_units_,
                  double(L.colpartial_elems) * sizeof(T) / 1e6);
 }
 
 template <typename T>
-void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2) {
+void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2, T out_scale) {
   if (colpartial_.size() == 0) colpartial_.alloc(ctx_, colpartial_elems_);
   RepSymArgs<T> a;
   a.pos = pos;
@@ -439,23 +485,26 @@ void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2) {
   a.partial = partial_.get();
   a.colpartial = colpartial_.get();
   a.blocks = blocks_.get();
+  a.tiles = tiles_.get();
   a.ld = ld_;
   a.total_units = std::max<long long>(total_units_, 1);
   a.nblocks = nblocks_;
   a.rows_per_block = threads_ * ipt_;
-  a.gb0 = gb0_;
   a.eps2 = eps2;
+  a.out_scale = out_scale;
   if (nblocks_ > 0 && total_units_ > 0) {
     void* args[] = {(void*)&a};
     GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_), dim3(grid_), dim3(threads_), args,
                              sym_smem<T>(dim_, threads_), ctx_->stream));
     ctx_->launches++;
   }
-  const unsigned rgrid = (unsigned)((ld_ + 255) / 256);
-  if (dim_ == 2) k_sym_reduce<T, 2><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_);
-  else k_sym_reduce<T, 3><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_);
-  GE_CUDA(cudaGetLastError());
-  ctx_->launches++;
+  if (reduce_len_ > 0) {
+    const unsigned rgrid = (unsigned)((reduce_len_ + 255) / 256);
+    if (dim_ == 2) k_sym_reduce<T, 2><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_, reduce_len_);
+    else k_sym_reduce<T, 3><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_, reduce_len_);
+    GE_CUDA(cudaGetLastError());
+    ctx_->launches++;
+  }
 }
 
 template class RepulsionSymPlan<double>;

@@ -520,7 +520,11 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   }
   // ---- grid tier ---------------------------------------------------------------------------
   DevBuf<T> d_pos0, d_pos1, d_Frep, d_Fprev;
+  cudaEvent_t tier_ev[2] = {nullptr, nullptr};
   if (!segs.empty()) {
+    GE_CUDA(cudaEventCreate(&tier_ev[0]));
+    GE_CUDA(cudaEventCreate(&tier_ev[1]));
+    GE_CUDA(cudaEventRecord(tier_ev[0], ctx->stream));
     d_segs.upload(ctx, segs.data(), segs.size());
     d_pos0.alloc(ctx, (size_t)dim * ld);
     d_pos1.alloc(ctx, (size_t)dim * ld);
@@ -535,16 +539,32 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     else k_ml_gather_pos<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_init.get(), d_vtx.get(), grid_slots, ld, d_pos0.get());
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
-    std::vector<RowSegment> rsegs;
-    for (auto& sg : segs)
-      rsegs.push_back(RowSegment{sg.x, sg.x + sg.y, sg.x, (int)round_up((int64_t)sg.x + sg.y, kTileJ)});
-    RepulsionPlan<T> rep(ctx, dim, rsegs);
+    // Repulsion plan of the tier: from a few million pairs per iteration on, every unordered pair
+    // inside an aggregate is evaluated once (k_repulsion_sym over one segment per aggregate);
+    // small tiers keep the ordered sweep with its fine-grained units.
+    double tier_pairs = 0.0;
+    for (auto& sg : segs) tier_pairs += double(sg.y) * double(sg.y - 1);
+    const bool use_sym = tier_pairs >= 1e6 * env_int("GE_ML_SYM_MIN_MPAIRS", 8) && env_int("GE_ML_SYM", 1) != 0;
+    std::unique_ptr<RepulsionPlan<T>> rep;
+    std::unique_ptr<RepulsionSymPlan<T>> sym;
+    if (use_sym) {
+      std::vector<SymSegment> ssegs;
+      for (auto& sg : segs) ssegs.push_back(SymSegment{sg.x, sg.x + sg.y});
+      sym.reset(new RepulsionSymPlan<T>(ctx, dim, ld, ssegs));
+    } else {
+      std::vector<RowSegment> rsegs;
+      for (auto& sg : segs)
+        rsegs.push_back(RowSegment{sg.x, sg.x + sg.y, sg.x, (int)round_up((int64_t)sg.x + sg.y, kTileJ)});
+      rep.reset(new RepulsionPlan<T>(ctx, dim, rsegs));
+    }
     T* pos[2] = {d_pos0.get(), d_pos1.get()};
     int cur = 0;
     const int iters = forces_only ? 1 : p.iterations;
     const double avg_deg = grid_slots > 0 ? double(nnz) / std::max(n, 1) : 0.0;
-    for (int it = 0; it < iters; ++it) {
-      rep.launch(pos[cur], d_mass.get(), ld, d_Frep.get(), ld, 0, oa.ph.repel, oa.ph.eps2);
+    const int group = group_for_degree(avg_deg);
+    auto one_iteration = [&]() {
+      if (sym) sym->launch(pos[cur], d_mass.get(), d_Frep.get(), oa.ph.eps2, oa.ph.repel);
+      else rep->launch(pos[cur], d_mass.get(), ld, d_Frep.get(), ld, 0, oa.ph.repel, oa.ph.eps2);
       StepArgs<T> sa;
       sa.e_begin = d_eb.get();
       sa.e_end = d_ee.get();
@@ -562,9 +582,33 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
       sa.nrows = grid_slots;
       sa.update = forces_only ? 0 : 1;
       sa.ph = oa.ph;
-      launch_attract_step<T>(ctx, sa, dim, group_for_degree(avg_deg), true);
+      launch_attract_step<T>(ctx, sa, dim, group, true);
       if (!forces_only) cur ^= 1;
+    };
+    int it = 0;
+    // The iterations of a tier are 3-4 short launches each: the steady-state pair of iterations
+    // (the position buffers ping-pong) is captured once and replayed.
+    if (iters >= 8 && std::getenv("GE_NO_GRAPH") == nullptr) {
+      for (; it < 2; ++it) one_iteration();
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      const int64_t launches_before = ctx->launches;
+      GE_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      one_iteration();
+      one_iteration();
+      GE_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+      const int64_t per_replay = ctx->launches - launches_before;
+      ctx->launches = launches_before;
+      GE_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      for (; it + 2 <= iters; it += 2) {
+        GE_CUDA(cudaGraphLaunch(exec, ctx->stream));
+        ctx->launches += per_replay;
+      }
+      GE_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaGraphExecDestroy(exec);
+      cudaGraphDestroy(graph);
     }
+    for (; it < iters; ++it) one_iteration();
     if (forces_only) {
       if (dim == 2) k_ml_scatter_forces<T, 2><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
       else k_ml_scatter_forces<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
@@ -574,11 +618,18 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     }
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
+    GE_CUDA(cudaEventRecord(tier_ev[1], ctx->stream));
   }
 
   lap("solve kernels");
   d_out.download(ctx, coords_out, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (tier_ev[0] != nullptr) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, tier_ev[0], tier_ev[1]) == cudaSuccess) ctx->grid_tier_ms += ms;
+    cudaEventDestroy(tier_ev[0]);
+    cudaEventDestroy(tier_ev[1]);
+  }
   lap("download");
 }
 

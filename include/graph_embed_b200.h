@@ -85,6 +85,8 @@ typedef struct ge_embed_stats {
   double pair_interactions; /* ordered pairs x iterations, all levels */
   double edge_visits;       /* CSR entries x iterations, all levels */
   int64_t kernel_launches;
+  double grid_tier_ms;    /* device time of the multi-CTA tier (aggregates > 512 members), all levels */
+  double device_radii_ms; /* device time of the ball-radius / rescale kernels, all levels */
 } ge_embed_stats;
 
 typedef struct ge_context ge_context;     /* device, stream, scratch */

@@ -290,14 +290,17 @@ static void ml_forces(int a, int s, const int* v, const double* deg, const int* 
  * the forces computed in iteration number `forces_iter` (0-based) and
  * fscale_at (n) the matching conditioning scales.
  */
-void oracle_multilevel_run(int n, const int* I, const int* J, const double* D, int m,
-                           const int* PI, const int* PJ, const int* v_A, const double* coords_A,
-                           const double* r_A, int dim, const double* init, const fa_params* p,
-                           double* coords_out, int forces_iter, double* forces_at,
-                           double* fscale_at) {
+void oracle_multilevel_run_range(int n, const int* I, const int* J, const double* D, int m,
+                                 const int* PI, const int* PJ, const int* v_A,
+                                 const double* coords_A, const double* r_A, int dim,
+                                 const double* init, const fa_params* p, double* coords_out,
+                                 int forces_iter, double* forces_at, double* fscale_at,
+                                 int a_begin, int a_end) {
   double* coords = coords_out;
   (void)n;
-  for (int a = 0; a < m; a++) {
+  (void)m;
+  /* the aggregates are independent (:340-341): a sub-range leaves the other rows untouched */
+  for (int a = a_begin; a < a_end; a++) {
     const int* v = PJ + PI[a];
     int s = PI[a + 1] - PI[a];
     for (int i = 0; i < s; i++)
@@ -347,6 +350,15 @@ void oracle_multilevel_run(int n, const int* I, const int* J, const double* D, i
     free(forces);
     free(forces_prev);
   }
+}
+
+void oracle_multilevel_run(int n, const int* I, const int* J, const double* D, int m,
+                           const int* PI, const int* PJ, const int* v_A, const double* coords_A,
+                           const double* r_A, int dim, const double* init, const fa_params* p,
+                           double* coords_out, int forces_iter, double* forces_at,
+                           double* fscale_at) {
+  oracle_multilevel_run_range(n, I, J, D, m, PI, PJ, v_A, coords_A, r_A, dim, init, p, coords_out,
+                              forces_iter, forces_at, fscale_at, 0, m);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -106,7 +106,7 @@ def vertex_to_aggregate(P_T):
     return v_A
 
 
-def multilevel_run(A, P_T, coords_A, r_A, dim, init, params, forces_iter=None):
+def multilevel_run(A, P_T, coords_A, r_A, dim, init, params, forces_iter=None, aggregates=None):
     """forceAtlasMultilevel (include/forceatlas.hpp:314-574) from caller-supplied init.
 
     init: n x dim by global vertex id.  Returns coords, or (coords, forces, fscale) of
@@ -120,9 +120,10 @@ def multilevel_run(A, P_T, coords_A, r_A, dim, init, params, forces_iter=None):
     F = S = None
     if forces_iter is not None:
         F, S = np.zeros((n, dim)), np.zeros(n)
-    oracle_lib().oracle_multilevel_run(n, _p(I), _p(J), _p(D), m, _p(PI), _p(PJ), _p(v_A), _p(cA),
-                                       _p(rA), dim, _p(x0), C.byref(params), _p(out),
-                                       int(forces_iter or 0), _p(F), _p(S))
+    a0, a1 = aggregates if aggregates is not None else (0, m)   # rows of other aggregates stay 0
+    oracle_lib().oracle_multilevel_run_range(n, _p(I), _p(J), _p(D), m, _p(PI), _p(PJ), _p(v_A), _p(cA),
+                                             _p(rA), dim, _p(x0), C.byref(params), _p(out),
+                                             int(forces_iter or 0), _p(F), _p(S), int(a0), int(a1))
     return out if forces_iter is None else (out, F, S)
 
 

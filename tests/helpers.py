@@ -77,3 +77,45 @@ def load_galerkin_golden(graphs):
         Cs.append(sp.csr_matrix((z["C%d_data" % l], z["C%d_indices" % l], z["C%d_indptr" % l]), shape=(m, m)))
         n = m
     return A, Ps, Cs, z
+
+
+_REFHIER_CACHE = {}
+
+
+def load_ref_hierarchy(graphs, name):
+    """A hierarchy produced by the REFERENCE's own partitioner (src/partitioner.cpp:1550-1893, call
+    shape of examples/embedder.cpp:187) on a synthetic graph of a BASELINE config, cached by
+    tests/golden/make_ref_hierarchy.py as the vertex->aggregate map of every level.  The graph is
+    regenerated from its seed and checked against the stored digest; the coarse graphs are the
+    Galerkin products examples/embedder.cpp:213-216 forms.  -> (As, P_Ts, meta)"""
+    import hashlib
+    if name in _REFHIER_CACHE:
+        return _REFHIER_CACHE[name]
+    z = np.load(os.path.join(GOLDEN, "refhier_%s.npz" % name))
+    kind, arg, seed = str(z["kind"]), int(z["arg"]), int(z["seed"])
+    if kind == "rmat":
+        A = graphs.rmat(arg, 16, seed=seed)
+    elif kind == "delaunay":
+        A = graphs.delaunay3d(arg, seed=seed)
+    elif kind == "rgg":
+        A = graphs.rgg(arg, 10.0, seed=seed)
+    else:
+        raise ValueError(kind)
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(A.indptr).tobytes())
+    h.update(np.ascontiguousarray(A.indices).tobytes())
+    assert h.hexdigest() == str(z["digest"]), "the generator no longer reproduces the cached graph"
+    Ps, n = [], A.shape[0]
+    for l in range(int(z["L"])):
+        agg = z["agg%d" % l]
+        assert agg.shape[0] == n
+        m = int(agg.max()) + 1
+        Ps.append(graphs.aggregation_matrix(agg, m))
+        Ps[-1] = sp.csr_matrix((Ps[-1].data, Ps[-1].indices.astype(np.int32),
+                                Ps[-1].indptr.astype(np.int32)), shape=Ps[-1].shape)
+        n = m
+    As = graphs.hierarchy_from(A, Ps)
+    meta = dict(kind=kind, arg=arg, seed=seed, cf=float(z["cf"]),
+                partition_seconds=float(z["partition_seconds"]))
+    _REFHIER_CACHE[name] = (As, Ps, meta)
+    return As, Ps, meta

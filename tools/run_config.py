@@ -1,5 +1,10 @@
 """One-off full-size runs of the BASELINE configs through ge_embed (single GPU):
-  python tools/run_config.py config3 | config5 [n_points] | config2 | config1
+  python tools/run_config.py config3 | config5 [n_points] | config2 | config1  [--ref] [--cpu-ref]
+--ref      use the hierarchy of the REFERENCE's partitioner cached under tests/golden/refhier_*.npz
+           (config3: R-MAT-20; config5: Delaunay of n_points = 1000000 or 4000000) instead of the
+           stand-in generator graphs.coarsen
+--cpu-ref  also time the compiled reference's embed() (oracle/_ref, all host threads) on the same
+           hierarchy -- minutes of CPU
 Prints one JSON line: hierarchy shape, embed() wall time, per-phase times, properties."""
 import json
 import os
@@ -29,14 +34,25 @@ def build(name, arg):
 
 
 def main():
-    name = sys.argv[1]
-    arg = sys.argv[2] if len(sys.argv) > 2 else None
+    flags = [a for a in sys.argv[1:] if a.startswith("--")]
+    pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+    name = pos[0]
+    arg = pos[1] if len(pos) > 1 else None
+    use_ref = "--ref" in flags
     t = time.time()
-    A, cf, dim = build(name, arg)
-    t_gen = time.time() - t
-    t = time.time()
-    As, Ps = graphs.coarsen(A, cf, min_coarse=64)
-    t_coarsen = time.time() - t
+    if use_ref:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import load_ref_hierarchy
+        key = {"config3": "rmat20", "config5": "delaunay%d" % int(arg or 4_000_000)}[name]
+        As, Ps, meta = load_ref_hierarchy(graphs, key)
+        A, cf, dim = As[0], meta["cf"], 3
+        t_gen, t_coarsen = time.time() - t, meta["partition_seconds"]
+    else:
+        A, cf, dim = build(name, arg)
+        t_gen = time.time() - t
+        t = time.time()
+        As, Ps = graphs.coarsen(A, cf, min_coarse=64)
+        t_coarsen = time.time() - t
     stats = graphs.level_stats(As, Ps)
     ctx = capi.Context(0)
     ctx.embed(As[-2:], Ps[-1:], dim, seed=1, coarse_iterations=100)  # warm-up (context, pool)
@@ -65,7 +81,23 @@ def main():
     cent /= np.diff(Ps[0].indptr)[:, None]
     spread = float(np.linalg.norm(x - cent[v_A], axis=1).mean())
     extent = float(np.linalg.norm(x - x.mean(0), axis=1).max())
-    out = {"config": name, "n": A.shape[0], "nnz": int(A.nnz), "dim": dim, "coarsening": cf,
+    cpu = None
+    if "--cpu-ref" in flags:
+        O = entry.load_oracle()
+        threads = len(os.sched_getaffinity(0))
+        fd = os.dup(1)
+        os.dup2(2, 1)   # the reference prints progress lines on stdout
+        try:
+            _, secs = O.ref_embed(As, Ps, dim, seed=1, nthreads=threads, kind="fast")
+        finally:
+            os.dup2(fd, 1)
+            os.close(fd)
+        cpu = {"embed_wall_s": secs, "threads": threads, "kind": "reference (oracle/_ref, -O3, OpenMP)"}
+    out = {"config": name, "hierarchy": ("reference partitioner (src/partitioner.cpp:1550-1893), cached"
+                                         if use_ref else "stand-in generator graphs.coarsen"),
+           "cpu_reference": cpu, "grid_tier_ms": st["grid_tier_ms"], "device_radii_ms": st["device_radii_ms"],
+           "grid_tier_share_of_levels": st["grid_tier_ms"] / max(st["levels_ms"], 1e-9),
+           "n": A.shape[0], "nnz": int(A.nnz), "dim": dim, "coarsening": cf,
            "levels": [s["n"] for s in stats], "max_aggregate": [s["max_size"] for s in stats],
            "pairs_per_iteration": [s["pairs"] for s in stats],
            "embed_wall_s": min(walls), "embed_wall_s_fixed_seed": wall_seeded, "coarse_ms": st["coarse_ms"], "levels_ms": st["levels_ms"],
