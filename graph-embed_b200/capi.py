@@ -71,7 +71,7 @@ SYMBOLS = [
     "ge_flat_plan_sync", "ge_flat_plan_select_kernels", "ge_flat_plan_profile", "ge_flat_plan_profile_get",
     "ge_flat_plan_create_symmetric", "ge_flat_plan_is_symmetric", "ge_flat_plan_pair_sums",
     "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
-    "ge_flat_symmetric_share", "ge_galerkin",
+    "ge_flat_symmetric_share", "ge_galerkin", "ge_level_radii_device",
 ]
 
 _lib = None
@@ -258,11 +258,28 @@ class Context:
         m = As[1].shape[0] if L else 0
         r_A, coords_A = np.zeros(max(m, 1)), np.zeros((max(m, 1), dim))
         stats = EmbedStats()
+        # embedMultilevel's out-parameters (level 1's radii / rescaled coordinates) are copied back
+        # only on request: partition::embed itself returns the finest coordinates alone
         _check(lib().ge_embed(self.h, L, a_arr, p_arr, int(dim), C.byref(opt), _ptr(out, _pd),
-                              _ptr(r_A, _pd), _ptr(coords_A, _pd), C.byref(stats)))
+                              _ptr(r_A, _pd) if return_level1 else None,
+                              _ptr(coords_A, _pd) if return_level1 else None, C.byref(stats)))
         if return_level1:
             return out, stats.as_dict(), r_A[:m], coords_A[:m]
         return out, stats.as_dict()
+
+    def level_radii(self, coords_A, dim, A_c=None, P_T_c=None, coords_Ac=None, r_Ac=None):
+        """src/embed.cpp:615-778 on the device (ge_level_radii_device) -> (coords_A, r_A)."""
+        cA = _f64(coords_A).reshape(-1, dim).copy()
+        m = cA.shape[0]
+        rA = np.zeros(m)
+        if P_T_c is None:
+            _check(lib().ge_level_radii_device(self.h, m, dim, _ptr(cA, _pd), _ptr(rA, _pd), None, None, None, None))
+        else:
+            Ac, Pc = CsrView(A_c), CsrView(P_T_c, with_data=False)
+            cAc, rAc = _f64(coords_Ac).reshape(-1, dim), _f64(r_Ac)
+            _check(lib().ge_level_radii_device(self.h, m, dim, _ptr(cA, _pd), _ptr(rA, _pd), Ac.ref(), Pc.ref(),
+                                               _ptr(cAc, _pd), _ptr(rAc, _pd)))
+        return cA, rA
 
     # -- parity hooks -------------------------------------------------------------------------
     def flat_forces(self, A, dim, coords, params, path=0):

@@ -428,10 +428,6 @@ void flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const
   s->download_coords(coords);
 }
 
-struct LevelOut {
-  std::vector<double> coords, r_A, coords_A;
-};
-
 struct EmbedRun {
   ge_context* ctx;
   int L, dim;
@@ -439,7 +435,6 @@ struct EmbedRun {
   const ge_csr* Ps;
   ge_embed_options opt;
   ge_embed_stats st{};
-  double* final_out = nullptr;  // level 0 is written straight into the caller's buffer
 
   // The level graphs are inputs that do not depend on any result: a helper thread uploads the
   // large ones on the copy stream while the coarsest-level solve (one long kernel that needs no
@@ -504,20 +499,85 @@ struct EmbedRun {
   }
   ~EmbedRun() {
     if (prefetcher.joinable()) prefetcher.join();
+    dx.clear();
+    dr.clear();
     // the prefetched buffers were allocated on the copy stream: nothing on the main stream may
     // still read them when they are returned to the pool
     if (!pre.empty()) cudaStreamSynchronize(ctx->stream);
   }
 
-  // embedMultilevel, src/embed.cpp:576-796.  Returns this level's coordinates; r_A / coords_A
-  // receive the radii and (rescaled) coordinates of level+1, as the reference's out-params do.
-  std::vector<double> level(int l, std::vector<double>& r_A, std::vector<double>& coords_A) {
+  // The level graph + slot layout on the device: uploaded ahead of time by the prefetcher (large
+  // levels) or here, on the main stream, when the level is first needed.
+  const PrefetchedGraph* graph(int l) {
+    if (pre.empty()) pre.resize(L);
+    if (pre[l]) return pre[l].get();
     const ge_csr& A = As[l];
-    const int n = A.rows;
-    if (l == L) {  // :582-587
-      if (opt.verbose) std::printf("embedding layer %d: getting base coords\n", l + opt.first_layer);
-      r_A.clear();
-      coords_A.clear();
+    std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
+    g->I.alloc(ctx, A.rows + 1);
+    g->J.alloc(ctx, (size_t)std::max<int64_t>(A.nnz, 1));
+    g->I.upload(ctx, A.indptr, A.rows + 1);
+    g->J.upload(ctx, A.indices, (size_t)A.nnz);
+    if (A.data != nullptr) {
+      g->Dw.alloc(ctx, (size_t)std::max<int64_t>(A.nnz, 1));
+      g->Dw.upload(ctx, A.data, (size_t)A.nnz);
+    }
+    g->layout = make_level_layout(ctx, Ps[l], A.rows);
+    GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
+    GE_CUDA(cudaEventRecord(g->ready, ctx->stream));
+    pre[l] = std::move(g);
+    return pre[l].get();
+  }
+
+  // Coordinates (dx[k]: n_k x dim) and ball radii (dr[k]: n_k) of every level stay on the device;
+  // only the finest level's coordinates (and, on request, level 1's radii / rescaled coordinates,
+  // the out-parameters of embedMultilevel) are copied back.
+  std::vector<DevBuf<double>> dx, dr;
+
+  // src/embed.cpp:615-778 for the vertices of level k = l + 1.
+  void radii(int k) {
+    const int m = As[k].rows;
+    dr[k].alloc(ctx, (size_t)std::max(m, 1));
+    const bool base = k == L;
+    const bool on_host = std::getenv("GE_HOST_RADII") != nullptr || (base && m > kRadiiBaseMax);
+    if (!on_host) {
+      if (base) {
+        level_radii_device(ctx, m, dim, dx[k].get(), dr[k].get(), nullptr, nullptr, nullptr);
+      } else {
+        GE_CUDA(cudaStreamWaitEvent(ctx->stream, graph(k)->ready, 0));
+        const RadiiLevel lv = radii_level_of(*graph(k), As[k + 1].rows);
+        level_radii_device(ctx, m, dim, dx[k].get(), dr[k].get(), &lv, dx[k + 1].get(), dr[k + 1].get());
+      }
+      return;
+    }
+    // host restatement (the checker of the device kernels; also the all-pairs base case of a
+    // coarsest level too large for the device's event arrays)
+    const double t0 = now_ms();
+    std::vector<double> x((size_t)m * dim), r(m, 0.0), xc, rc;
+    dx[k].download(ctx, x.data(), x.size());
+    if (!base) {
+      const int mc = As[k + 1].rows;
+      xc.resize((size_t)mc * dim);
+      rc.resize(mc);
+      dx[k + 1].download(ctx, xc.data(), xc.size());
+      dr[k + 1].download(ctx, rc.data(), rc.size());
+    }
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (base) level_radii(m, dim, x.data(), r.data(), nullptr, nullptr, nullptr, nullptr);
+    else level_radii(m, dim, x.data(), r.data(), &As[k], &Ps[k], xc.data(), rc.data());
+    dx[k].upload(ctx, x.data(), x.size());
+    dr[k].upload(ctx, r.data(), r.size());
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.host_radii_ms += now_ms() - t0;
+  }
+
+  // embedMultilevel, src/embed.cpp:576-796, unrolled from the coarsest level up.
+  void run(double* coords_out, double* r_A_out, double* coords_A_out) {
+    dx.resize(L + 1);
+    dr.resize(L + 1);
+    {  // :582-587 base: forceAtlas with its defaults on the coarsest graph
+      const ge_csr& A = As[L];
+      const int n = A.rows;
+      if (opt.verbose) std::printf("embedding layer %d: getting base coords\n", L + opt.first_layer);
       std::vector<double> coords((size_t)n * dim);
       reference_uniform(resolve_seed(opt.seed), (int64_t)n * dim, coords.data());  // forceatlas.hpp:118-125
       ge_params p;
@@ -525,58 +585,62 @@ struct EmbedRun {
       p.iterations = opt.coarse_iterations;
       p.precision = opt.precision;
       const double t0 = now_ms();
-      flat_solve(ctx, A, dim, coords.data(), p, 0);
+      if (L == 0) {
+        flat_solve(ctx, A, dim, coords.data(), p, 0);
+        std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
+      } else if (n >= 1 && n <= onchip_threshold()) {
+        onchip_flat_solve(ctx, A, dim, p, coords.data(), nullptr, false, &dx[L]);
+      } else {
+        flat_solve(ctx, A, dim, coords.data(), p, 0);
+        dx[L].alloc(ctx, (size_t)std::max(n, 1) * dim);
+        dx[L].upload(ctx, coords.data(), coords.size());
+      }
       st.coarse_ms += now_ms() - t0;
       join_prefetch();  // normally long finished: the solve above takes 0.1-0.2 s
       st.pair_interactions += double(n) * double(n - 1) * p.iterations;
       st.edge_visits += double(A.nnz) * p.iterations;
-      return coords;
     }
-    std::vector<double> r_Ac, coords_Ac;
-    coords_A = level(l + 1, r_Ac, coords_Ac);  // :593
-    const ge_csr& P = Ps[l];
-    const int m = P.rows;
-    if (opt.verbose) std::printf("embeding layer %d\n", l + opt.first_layer);
-    const double t0 = now_ms();
-    r_A.assign(m, 0.0);
-    if (r_Ac.empty())
-      level_radii(m, dim, coords_A.data(), r_A.data(), nullptr, nullptr, nullptr, nullptr);
-    else
-      level_radii(m, dim, coords_A.data(), r_A.data(), &As[l + 1], &Ps[l + 1], coords_Ac.data(), r_Ac.data());
-    st.host_radii_ms += now_ms() - t0;
-
-    const PrefetchedGraph* pg = (size_t)l < pre.size() ? pre[l].get() : nullptr;
-    std::vector<int32_t> v_A;  // :605 (already on the device when the level was prepared ahead)
-    if (pg == nullptr || pg->layout == nullptr) {
-      v_A.resize(n);
-      for (int a = 0; a < m; ++a)
-        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) v_A[P.indices[c]] = a;
+    for (int l = L - 1; l >= 0; --l) {
+      const ge_csr& A = As[l];
+      const ge_csr& P = Ps[l];
+      const int n = A.rows;
+      if (opt.verbose) std::printf("embeding layer %d\n", l + opt.first_layer);
+      radii(l + 1);
+      if (l + 2 <= L) {  // the grand-parent level is not needed any more
+        dx[l + 2].release();
+        dr[l + 2].release();
+      }
+      // Initial local coordinates: with a fixed seed, the reference's own stream in its draw order
+      // (forceatlas.hpp:341, 356-358); with seed 0 (the reference's std::random_device mode, where
+      // any stream is as good as another) they are drawn on the device.
+      std::vector<double> init;
+      if (opt.seed != 0) {
+        init.resize((size_t)n * dim);
+        level_init_stream(opt.seed, P, dim, init.data());
+      }
+      ge_params p;
+      ge_params_default_multilevel(&p);
+      p.iterations = opt.level_iterations;  // :793
+      p.precision = opt.precision;
+      p.seed = opt.seed;
+      LevelIO io;
+      io.d_coords_A = dx[l + 1].get();
+      io.d_r_A = dr[l + 1].get();
+      io.keep_out = l > 0 ? &dx[l] : nullptr;
+      io.download = l == 0;  // the finest level goes straight into the caller's buffer
+      const double t1 = now_ms();
+      double pairs = 0.0;
+      multilevel_solve(ctx, A, P, nullptr, nullptr, nullptr, init.empty() ? nullptr : init.data(),
+                       l == 0 ? coords_out : nullptr, dim, p, false, &pairs, 0, -1, graph(l), &io);
+      st.levels_ms += now_ms() - t1;
+      st.pair_interactions += pairs * p.iterations;
+      st.edge_visits += double(A.nnz) * p.iterations;
     }
-    // Initial local coordinates: with a fixed seed, the reference's own stream in its draw order
-    // (forceatlas.hpp:341, 356-358); with seed 0 (the reference's std::random_device mode, where
-    // any stream is as good as another) they are drawn on the device.
-    std::vector<double> init;
-    if (opt.seed != 0) {
-      init.resize((size_t)n * dim);
-      level_init_stream(opt.seed, P, dim, init.data());
+    if (L > 0) {  // what embedMultilevel leaves in its r_A / coords_A out-parameters
+      if (r_A_out) dr[1].download(ctx, r_A_out, (size_t)As[1].rows);
+      if (coords_A_out) dx[1].download(ctx, coords_A_out, (size_t)As[1].rows * dim);
+      if (r_A_out || coords_A_out) GE_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    ge_params p;
-    ge_params_default_multilevel(&p);
-    p.iterations = opt.level_iterations;  // :793
-    p.precision = opt.precision;
-    p.seed = opt.seed;
-    // the finest level (possibly hundreds of MB) goes straight into the caller's buffer
-    const bool direct = l == 0 && final_out != nullptr;
-    std::vector<double> coords(direct ? 0 : (size_t)n * dim);
-    const double t1 = now_ms();
-    double pairs = 0.0;
-    multilevel_solve(ctx, A, P, v_A.empty() ? nullptr : v_A.data(), coords_A.data(), r_A.data(),
-                     init.empty() ? nullptr : init.data(), direct ? final_out : coords.data(), dim, p,
-                     false, &pairs, 0, -1, pg);
-    st.levels_ms += now_ms() - t1;
-    st.pair_interactions += pairs * p.iterations;
-    st.edge_visits += double(A.nnz) * p.iterations;
-    return coords;
   }
 };
 
@@ -784,14 +848,8 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     ctx->grid_tier_ms = 0;
     ctx->radii_ms = 0;
     const double t0 = now_ms();
-    std::vector<double> r_A, coords_A;
-    run.final_out = n_levels > 0 ? coords_out : nullptr;
     run.start_prefetch();
-    std::vector<double> coords = run.level(0, r_A, coords_A);
-    if (!coords.empty()) std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
-    if (r_A_out && !r_A.empty()) std::memcpy(r_A_out, r_A.data(), r_A.size() * sizeof(double));
-    if (coords_A_out && !coords_A.empty())
-      std::memcpy(coords_A_out, coords_A.data(), coords_A.size() * sizeof(double));
+    run.run(coords_out, r_A_out, coords_A_out);
     run.st.total_ms = now_ms() - t0;
     run.st.kernel_launches = ctx->launches - launches0;
     run.st.h2d_bytes = ctx->h2d_bytes - h0;
@@ -847,6 +905,44 @@ ge_status ge_level_radii(int m, int dim, double* coords_A, double* r_A, const ge
       GE_REQUIRE(P_T_c->cols == m && A_c->rows == m, "shape mismatch");
     }
     level_radii(m, dim, coords_A, r_A, A_c, P_T_c, coords_Ac, r_Ac);
+  });
+}
+
+ge_status ge_level_radii_device(ge_context* ctx, int m, int dim, double* coords_A, double* r_A,
+                                const ge_csr* A_c, const ge_csr* P_T_c, const double* coords_Ac,
+                                const double* r_Ac) {
+  return guarded([&] {
+    require_ctx(ctx);
+    GE_REQUIRE(m >= 0 && (dim == 2 || dim == 3) && coords_A && r_A, "bad argument");
+    if (m == 0) return;
+    DevBuf<double> d_x(ctx, (size_t)m * dim), d_r(ctx, (size_t)m), d_xc, d_rc;
+    d_x.upload(ctx, coords_A, (size_t)m * dim);
+    if (P_T_c == nullptr) {
+      level_radii_device(ctx, m, dim, d_x.get(), d_r.get(), nullptr, nullptr, nullptr);
+    } else {
+      check_csr(A_c, "A_c");
+      check_csr(P_T_c, "P_T_c");
+      GE_REQUIRE(coords_Ac && r_Ac, "coarse centres / radii are null");
+      GE_REQUIRE(P_T_c->cols == m && A_c->rows == m, "shape mismatch");
+      GE_REQUIRE(P_T_c->indptr[P_T_c->rows] == m, "P_T_c must list every vertex exactly once");
+      const int mc = P_T_c->rows;
+      PrefetchedGraph g;
+      g.I.alloc(ctx, (size_t)m + 1);
+      g.J.alloc(ctx, (size_t)std::max<int64_t>(A_c->nnz, 1));
+      g.I.upload(ctx, A_c->indptr, (size_t)m + 1);
+      g.J.upload(ctx, A_c->indices, (size_t)A_c->nnz);
+      g.layout = make_level_layout(ctx, *P_T_c, m);
+      d_xc.alloc(ctx, (size_t)std::max(mc, 1) * dim);
+      d_rc.alloc(ctx, (size_t)std::max(mc, 1));
+      d_xc.upload(ctx, coords_Ac, (size_t)mc * dim);
+      d_rc.upload(ctx, r_Ac, (size_t)mc);
+      const RadiiLevel lv = radii_level_of(g, mc);
+      level_radii_device(ctx, m, dim, d_x.get(), d_r.get(), &lv, d_xc.get(), d_rc.get());
+      GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    d_x.download(ctx, coords_A, (size_t)m * dim);
+    d_r.download(ctx, r_A, (size_t)m);
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
 

@@ -140,7 +140,7 @@ constexpr int kOnchipMaxThreads = 1024;
 constexpr int kOnchipMaxVertices = 1024;
 void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
                        double* coords /* n x dim in/out */, double* forces_out /* or null */,
-                       bool forces_only);
+                       bool forces_only, DevBuf<double>* keep_on_device = nullptr /* [n][dim]: no download */);
 
 // ---- ge_multilevel.cu ------------------------------------------------------------------------
 // A level graph already on the device (uploaded ahead of time on another stream); `ready` is
@@ -158,11 +158,41 @@ struct PrefetchedGraph {
     free_level_layout(layout);
   }
 };
+// Device-resident inputs / outputs of one level (ge_embed keeps the coordinates on the device
+// between the levels): when d_coords_A / d_r_A are set the host pointers coords_A / r_A of
+// multilevel_solve are ignored; keep_out receives the level's coordinates [n][dim]; download =
+// false skips the copy to coords_out.
+struct LevelIO {
+  const double* d_coords_A = nullptr;
+  const double* d_r_A = nullptr;
+  DevBuf<double>* keep_out = nullptr;
+  bool download = true;
+};
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
                       double* pairs_out, int agg_begin = 0, int agg_end = -1,
-                      const PrefetchedGraph* pre = nullptr);
+                      const PrefetchedGraph* pre = nullptr, const LevelIO* io = nullptr);
+
+// ---- ge_radii.cu --------------------------------------------------------------------------------
+// Ball radii + rescale on the device (src/embed.cpp:615-778).  d_x [m][dim] in/out, d_r [m] out.
+// lv == nullptr: base case (all pairs of the m vertices, :616-679).  Otherwise the general case
+// (:680-777): lv describes the level whose m vertices these are -- its graph (I, J), the vertex ->
+// family map `parent`, the families' member lists (PI, PJ: the CSR of its aggregation, mc rows) --
+// and d_xc [mc][dim] / d_rc [mc] are the centres and radii of the families' balls.
+constexpr int kRadiiBaseMax = 4096;
+struct RadiiLevel {
+  const int* I;
+  const int* J;
+  const int* parent;
+  const int* PI;
+  const int* PJ;
+  int mc;
+};
+void level_radii_device(ge_context* ctx, int m, int dim, double* d_x, double* d_r,
+                        const RadiiLevel* lv, const double* d_xc, const double* d_rc);
+// The RadiiLevel view of a level whose graph and slot layout are on the device.
+RadiiLevel radii_level_of(const PrefetchedGraph& g, int mc);
 
 // ---- ge_galerkin.cu ----------------------------------------------------------------------------
 int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, int32_t* c_indptr,

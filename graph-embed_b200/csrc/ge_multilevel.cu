@@ -257,6 +257,8 @@ struct LevelLayout {
   int64_t ld = 0;
   double pairs = 0.0;
   DevBuf<int> d_vA, d_vtx, d_slot_of, d_agg_base, d_agg_of_slot;
+  DevBuf<int> d_PI, d_PJ;  // the aggregation's CSR (member lists): the families of the radii step
+  int n = 0, m = 0;
 };
 
 namespace {
@@ -356,6 +358,14 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   L_.d_slot_of.upload(ctx, slot_of.data(), n);
   L_.d_agg_base.upload(ctx, agg_base.data(), m);
   L_.d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
+  if (!forces_only && agg_begin == 0 && agg_end == m) {
+    L_.d_PI.alloc(ctx, (size_t)m + 1);
+    L_.d_PJ.alloc(ctx, (size_t)std::max(n, 1));
+    L_.d_PI.upload(ctx, P.indptr, (size_t)m + 1);
+    L_.d_PJ.upload(ctx, P.indices, (size_t)n);
+  }
+  L_.n = n;
+  L_.m = m;
   // (copies from pageable memory have left the host arrays when cudaMemcpyAsync returns)
 }
 
@@ -363,7 +373,8 @@ template <typename T>
 void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32_t* v_A,
                   const double* coords_A, const double* r_A, const double* init,
                   double* coords_out, int dim, const ge_params& p, bool forces_only,
-                  double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
+                  double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre,
+                  const LevelIO* io) {
   constexpr int NM = Real<T>::kMassArrays;
   const int n = A.rows, m = P.rows;
   const int nnz = A.indptr[n];
@@ -397,7 +408,12 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   lap("host layout");
   // ---- upload ------------------------------------------------------------------------------
   DevBuf<int> d_I, d_J, d_eb(ctx, (size_t)ld), d_ee(ctx, (size_t)ld), d_eidx(ctx, std::max(nnz, 1));
-  DevBuf<double> d_Dw, d_cA(ctx, (size_t)std::max(m, 1) * dim), d_rA(ctx, std::max(m, 1)), d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
+  const bool dev_in = io != nullptr && io->d_coords_A != nullptr;
+  DevBuf<double> d_Dw, d_cA, d_rA, d_init(ctx, (size_t)std::max(n, 1) * dim), d_out(ctx, (size_t)std::max(n, 1) * dim);
+  if (!dev_in) {
+    d_cA.alloc(ctx, (size_t)std::max(m, 1) * dim);
+    d_rA.alloc(ctx, std::max(m, 1));
+  }
   DevBuf<T> d_mass(ctx, (size_t)NM * ld), d_E(ctx, (size_t)dim * ld), d_ew;
   const int* dI;
   const int* dJ;
@@ -421,8 +437,12 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
     dJ = d_J.get();
   }
   if (weighted) d_ew.alloc(ctx, std::max(nnz, 1));
-  d_cA.upload(ctx, coords_A, (size_t)m * dim);
-  d_rA.upload(ctx, r_A, m);
+  if (!dev_in) {
+    d_cA.upload(ctx, coords_A, (size_t)m * dim);
+    d_rA.upload(ctx, r_A, m);
+  }
+  const double* dcA = dev_in ? io->d_coords_A : d_cA.get();
+  const double* drA = dev_in ? io->d_r_A : d_rA.get();
   if (init != nullptr) {
     d_init.upload(ctx, init, (size_t)n * dim);
   } else {
@@ -446,7 +466,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   pa.vtx = d_vtx.get();
   pa.slot_of = d_slot_of.get();
   pa.agg_base = d_agg_base.get();
-  pa.cA = d_cA.get();
+  pa.cA = dcA;
   pa.mass = d_mass.get();
   pa.Eext = d_E.get();
   pa.e_begin = d_eb.get();
@@ -478,8 +498,8 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   oa.e_w = weighted ? d_ew.get() : nullptr;
   oa.Eext = d_E.get();
   oa.ld = ld;
-  oa.cA_aos = d_cA.get();
-  oa.rA = d_rA.get();
+  oa.cA_aos = dcA;
+  oa.rA = drA;
   oa.out_aos = d_out.get();
   oa.iters = p.iterations;
   oa.forces_only = forces_only ? 1 : 0;
@@ -490,11 +510,11 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   if (n_single > 0) {
     const unsigned grid = (unsigned)((n_single + 255) / 256);
     if (dim == 2)
-      k_ml_singletons<2><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), d_cA.get(),
-                                                        d_rA.get(), single_begin, n_single, d_out.get());
+      k_ml_singletons<2><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), dcA,
+                                                        drA, single_begin, n_single, d_out.get());
     else
-      k_ml_singletons<3><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), d_cA.get(),
-                                                        d_rA.get(), single_begin, n_single, d_out.get());
+      k_ml_singletons<3><<<grid, 256, 0, ctx->stream>>>(d_vtx.get(), d_vA.get(), dcA,
+                                                        drA, single_begin, n_single, d_out.get());
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -613,8 +633,8 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
       if (dim == 2) k_ml_scatter_forces<T, 2><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
       else k_ml_scatter_forces<T, 3><<<ggrid, 256, 0, ctx->stream>>>(d_Fprev.get(), d_vtx.get(), grid_slots, ld, d_out.get());
     } else {
-      if (dim == 2) k_ml_segment_epilogue<T, 2><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), d_cA.get(), d_rA.get(), d_out.get());
-      else k_ml_segment_epilogue<T, 3><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), d_cA.get(), d_rA.get(), d_out.get());
+      if (dim == 2) k_ml_segment_epilogue<T, 2><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), dcA, drA, d_out.get());
+      else k_ml_segment_epilogue<T, 3><<<(unsigned)segs.size(), 1024, 0, ctx->stream>>>(pos[cur], ld, d_segs.get(), d_vtx.get(), dcA, drA, d_out.get());
     }
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -622,8 +642,9 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   }
 
   lap("solve kernels");
-  d_out.download(ctx, coords_out, (size_t)n * dim);
+  if (io == nullptr || io->download) d_out.download(ctx, coords_out, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (io != nullptr && io->keep_out != nullptr) *io->keep_out = std::move(d_out);
   if (tier_ev[0] != nullptr) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, tier_ev[0], tier_ev[1]) == cudaSuccess) ctx->grid_tier_ms += ms;
@@ -642,10 +663,23 @@ LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n) {
 }
 void free_level_layout(LevelLayout* layout) { delete layout; }
 
+RadiiLevel radii_level_of(const PrefetchedGraph& g, int mc) {
+  GE_REQUIRE(g.layout != nullptr && g.layout->d_PI.size() > 0, "level layout without member lists");
+  RadiiLevel lv;
+  lv.I = g.I.get();
+  lv.J = g.J.get();
+  lv.parent = g.layout->d_vA.get();
+  lv.PI = g.layout->d_PI.get();
+  lv.PJ = g.layout->d_PJ.get();
+  lv.mc = mc;
+  return lv;
+}
+
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,
                       double* coords_out, int dim, const ge_params& p, bool forces_only,
-                      double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre) {
+                      double* pairs_out, int agg_begin, int agg_end, const PrefetchedGraph* pre,
+                      const LevelIO* io) {
   if (agg_end < 0) agg_end = P_T.rows;
   GE_REQUIRE(0 <= agg_begin && agg_begin <= agg_end && agg_end <= P_T.rows, "bad aggregate range");
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
@@ -653,9 +687,9 @@ void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const
   GE_REQUIRE(P_T.cols == A.rows, "P_T.cols must equal A.rows");
   GE_REQUIRE(P_T.indptr[P_T.rows] == A.rows, "P_T must list every vertex exactly once");
   if (p.precision == GE_F32)
-    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre);
+    multilevel_t<float>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre, io);
   else
-    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre);
+    multilevel_t<double>(ctx, A, P_T, v_A, coords_A, r_A, init, coords_out, dim, p, forces_only, pairs_out, agg_begin, agg_end, pre, io);
 }
 
 }  // namespace ge

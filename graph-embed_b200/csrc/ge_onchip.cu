@@ -776,7 +776,7 @@ int onchip_thread_budget(int n) {
 
 template <typename T>
 void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p, double* coords,
-                   double* forces_out, bool forces_only) {
+                   double* forces_out, bool forces_only, DevBuf<double>* keep) {
   const int n = A.rows;
   const int nnz = A.indptr[n];
   const bool weighted = p.use_weights && A.data != nullptr;
@@ -835,20 +835,21 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
     launch_onchip_cluster<T>(ctx, a, n, dim, csize);
   else
     launch_onchip_cta<T>(ctx, a, 1, dim, false, L, threads, n);
-  d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);
+  if (keep == nullptr) d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (keep != nullptr) *keep = std::move(d_out);
 }
 
 }  // namespace
 
 void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
-                       double* coords, double* forces_out, bool forces_only) {
+                       double* coords, double* forces_out, bool forces_only, DevBuf<double>* keep) {
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
   GE_REQUIRE(A.rows >= 1 && A.rows <= kOnchipMaxVertices, "on-chip flat solve needs 1..1024 vertices");
   if (p.precision == GE_F32)
-    onchip_flat_t<float>(ctx, A, dim, p, coords, forces_out, forces_only);
+    onchip_flat_t<float>(ctx, A, dim, p, coords, forces_out, forces_only, keep);
   else
-    onchip_flat_t<double>(ctx, A, dim, p, coords, forces_out, forces_only);
+    onchip_flat_t<double>(ctx, A, dim, p, coords, forces_out, forces_only, keep);
 }
 
 }  // namespace ge

@@ -1,0 +1,406 @@
+// graph-embed_b200 :: ball radii + rescale between levels on the device.
+//
+// Replaces the host loop of partition::embedMultilevel, /root/reference/src/embed.cpp:615-778
+// (duplicated at :166-329): the radius r_A of every vertex of level l+1 -- the ball inside which
+// its members will be placed at level l -- and the shrink of that level's coordinates / radii into
+// the balls of level l+2.
+//
+// The reference keeps, per family (= the members of one aggregate of level l+2, or every vertex in
+// the base case), a vector of events (t, i, j) "balls i and j touch", t = -|xi - xj| / 2, sorts it,
+// pops the back, freezes the endpoint(s) that are still growing at radius -t, re-keys the events
+// that touch a ball that just froze (t' = -(2(-t) - radius): the partner covers the rest alone) and
+// sorts again.  Here: one CTA per family, the events in global memory, and per pop ONE pass of the
+// CTA over the family's live events that applies the pending re-keys, drops events whose two ends
+// are frozen, and finds the next event to pop as the lexicographic maximum of (t, i, j) -- exactly
+// the element std::sort puts at the back.  Same arithmetic (IEEE add / mul / sqrt, no FMA
+// contraction), same tie-breaking, same `r <= 0 means still growing` test as the host restatement
+// ge_level_radii, which stays as the checker: the results are bit-identical.
+//
+// The coordinates never leave the device: ge_embed chains  solve(l+1) -> radii -> solve(l).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ge_context.h"
+
+namespace ge {
+
+namespace {
+
+__device__ __forceinline__ double dist_rn(const double* a, const double* b, int dim) {
+  double sum = 0.0;
+  for (int k = 0; k < dim; ++k) {
+    const double d = __dsub_rn(b[k], a[k]);
+    sum = __dadd_rn(sum, __dmul_rn(d, d));
+  }
+  return __dsqrt_rn(sum);
+}
+
+// ---- event lists -------------------------------------------------------------------------------
+// Base case (:616-634): every pair i < j of the m vertices.
+__global__ void k_radii_events_base(int m, int dim, const double* __restrict__ x,
+                                    double* __restrict__ ev_t, int2* __restrict__ ev_ij) {
+  const int i = blockIdx.x;
+  const long long off = (long long)i * (2LL * m - i - 1) / 2;
+  for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
+    const long long e = off + (j - i - 1);
+    ev_t[e] = -dist_rn(x + (size_t)i * dim, x + (size_t)j * dim, dim) / 2;
+    ev_ij[e] = make_int2(i, j);
+  }
+}
+
+// General case (:686-706): the edges a < j of A_c whose two ends have the same parent.  One warp
+// per member position c of P_T_c (family-major order, so a family's events are contiguous).
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_radii_events(int m, int dim, const int* __restrict__ I,
+                                                      const int* __restrict__ J,
+                                                      const int* __restrict__ parent,
+                                                      const int* __restrict__ PJ,
+                                                      const double* __restrict__ x,
+                                                      int* __restrict__ count,
+                                                      const int* __restrict__ ev_off,
+                                                      double* __restrict__ ev_t,
+                                                      int2* __restrict__ ev_ij) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= m) return;
+  const int a = PJ[c];
+  const int pa = parent[a];
+  const int rb = I[a], re = I[a + 1];
+  int cnt = 0;
+  const int base = FILL ? ev_off[c] : 0;
+  for (int e0 = rb; e0 < re; e0 += 32) {
+    const int e = e0 + lane;
+    const int j = e < re ? J[e] : -1;
+    const bool take = j > a && parent[j] == pa;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (FILL && take) {
+      const int dst = base + cnt + __popc(mask & ((1u << lane) - 1u));
+      ev_t[dst] = -dist_rn(x + (size_t)a * dim, x + (size_t)j * dim, dim) / 2;
+      ev_ij[dst] = make_int2(a, j);
+    }
+    cnt += __popc(mask);
+  }
+  if (!FILL && lane == 0) count[c] = cnt;
+}
+
+// ---- exclusive scan (three small kernels; m is at most a few hundred thousand) -----------------
+constexpr int kScanBlock = 1024;
+__device__ __forceinline__ int block_scan_excl(int v, int* scratch, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int off = 1; off < 32; off <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += o;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += o;
+    }
+    scratch[lane] = w;
+  }
+  __syncthreads();
+  const int before = warp > 0 ? scratch[warp - 1] : 0;
+  total = scratch[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return before + inc - v;
+}
+__global__ void __launch_bounds__(kScanBlock) k_rscan_blocks(const int* __restrict__ in, int n,
+                                                            int* __restrict__ out, int* __restrict__ sums) {
+  __shared__ int scratch[32];
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  const int v = i < n ? in[i] : 0;
+  int total;
+  const int ex = block_scan_excl(v, scratch, total);
+  if (i < n) out[i] = ex;
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanBlock) k_rscan_sums(int* sums, int nb) {  // one CTA
+  __shared__ int scratch[32];
+  int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += kScanBlock) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nb ? sums[i] : 0;
+    int total;
+    const int ex = block_scan_excl(v, scratch, total);
+    if (i < nb) sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) sums[nb] = carry;  // grand total
+}
+__global__ void __launch_bounds__(kScanBlock) k_rscan_add(int* __restrict__ out, int n,
+                                                         const int* __restrict__ sums, int nb) {
+  const int i = blockIdx.x * kScanBlock + threadIdx.x;
+  if (i < n) out[i] += sums[blockIdx.x];
+  if (i == 0) out[n] = sums[nb];
+}
+
+// ---- the event loop ----------------------------------------------------------------------------
+struct GrowArgs {
+  int dim;
+  int general;             // 0: base case, one family = all vertices, no shrink
+  int m_limit;             // the reference's loop bound `count < m` (m = vertices of the level)
+  int nfam;
+  const int* PI;           // general: families = rows of P_T_c
+  const int* PJ;
+  const int* ev_off;       // general: per member position; base: {0, E}
+  double* ev_t;
+  int2* ev_ij;             // .x < 0: served or dead
+  double* x;               // [m][dim] in/out (shrunk in the general case)
+  double* r;               // [m] zero on entry
+  const double* xc;        // [mc][dim]
+  const double* rc;        // [mc]
+  long long E_base;
+  int class_split;         // families with more events than this run in the wide kernel
+};
+
+template <int THREADS, bool WIDE>
+__global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
+  constexpr int NW = THREADS / 32;
+  __shared__ double s_t[NW];
+  __shared__ int s_i[NW], s_j[NW];
+  __shared__ long long s_e[NW];
+  __shared__ double sh_reach;
+  __shared__ int sh_f0, sh_f1, sh_stop;
+  __shared__ double s_red[NW];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int c0 = 0, c1 = 0;
+  long long e0 = 0, e1 = 0;
+  if (g.general) {
+    c0 = g.PI[b];
+    c1 = g.PI[b + 1];
+    e0 = g.ev_off[c0];
+    e1 = g.ev_off[c1];
+  } else {
+    e1 = g.E_base;
+  }
+  const long long E = e1 - e0;
+  if ((E > g.class_split) != WIDE) return;
+  const int s = c1 - c0;
+  if (g.general && s == 0) return;
+
+  if (g.general && s == 1) {  // :687-691
+    if (tid == 0) g.r[g.PJ[c0]] = g.rc[b];
+  } else if (E > 0) {
+    int f0 = -1, f1 = -1;
+    double reach = 0.0;
+    long long count = 0;
+    for (;;) {
+      double bt = 0.0;
+      int bi = -1, bj = -1;
+      long long be = -1;
+      for (long long e = e0 + tid; e < e1; e += THREADS) {
+        const int2 ij = g.ev_ij[e];
+        if (ij.x < 0) continue;
+        double t = g.ev_t[e];
+        const bool hit0 = (ij.x == f0) | (ij.y == f0), hit1 = (ij.x == f1) | (ij.y == f1);
+        if (hit0 | hit1) {  // a ball this event touches froze at the last pop (:655-676, :732-753)
+          const int fz = hit0 ? f0 : f1;
+          const int other = ij.x == fz ? ij.y : ij.x;
+          t = -__dsub_rn(__dmul_rn(2.0, -t), reach);
+          if (__ldcg(&g.r[other]) > 0.0) {  // both ends frozen: can never act again
+            g.ev_ij[e] = make_int2(-1, -1);
+            continue;
+          }
+          g.ev_t[e] = t;
+        }
+        const bool better = be < 0 || t > bt || (t == bt && (ij.x > bi || (ij.x == bi && ij.y > bj)));
+        if (better) {
+          bt = t;
+          bi = ij.x;
+          bj = ij.y;
+          be = e;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        const long long oe = __shfl_xor_sync(0xffffffffu, be, off);
+        const bool better = oe >= 0 && (be < 0 || ot > bt || (ot == bt && (oi > bi || (oi == bi && oj > bj))));
+        if (better) {
+          bt = ot;
+          bi = oi;
+          bj = oj;
+          be = oe;
+        }
+      }
+      if (lane == 0) {
+        s_t[warp] = bt;
+        s_i[warp] = bi;
+        s_j[warp] = bj;
+        s_e[warp] = be;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < NW; ++w) {
+          const double ot = s_t[w];
+          const int oi = s_i[w], oj = s_j[w];
+          const long long oe = s_e[w];
+          const bool better = oe >= 0 && (be < 0 || ot > bt || (ot == bt && (oi > bi || (oi == bi && oj > bj))));
+          if (better) {
+            bt = ot;
+            bi = oi;
+            bj = oj;
+            be = oe;
+          }
+        }
+        int stop = 0, nf0 = -1, nf1 = -1;
+        double nreach = 0.0;
+        if (be < 0) {
+          stop = 1;  // no live event left
+        } else {
+          g.ev_ij[be] = make_int2(-1, -1);  // popped
+          const bool live_i = g.r[bi] <= 0.0, live_j = g.r[bj] <= 0.0;
+          if (live_i || live_j) {
+            nreach = -bt;
+            if (live_i) {
+              g.r[bi] = nreach;
+              nf0 = bi;
+            }
+            if (live_j) {
+              g.r[bj] = nreach;
+              nf1 = bj;
+            }
+            count += (live_i ? 1 : 0) + (live_j ? 1 : 0);
+            if (count >= g.m_limit) stop = 1;
+          }
+        }
+        sh_f0 = nf0;
+        sh_f1 = nf1;
+        sh_reach = nreach;
+        sh_stop = stop;
+      }
+      __syncthreads();
+      f0 = sh_f0;
+      f1 = sh_f1;
+      reach = sh_reach;
+      if (sh_stop) break;
+      // (the next pass starts with global loads; the barrier above also orders thread 0's writes)
+    }
+  }
+  if (!g.general) return;
+  __syncthreads();
+
+  // :757-777: shrink the family into the ball of its parent
+  const double* cb = g.xc + (size_t)b * g.dim;
+  double alpha = 0.0;
+  for (int c = c0 + tid; c < c1; c += THREADS) {
+    const int a = g.PJ[c];
+    const double v = __dadd_rn(dist_rn(cb, g.x + (size_t)a * g.dim, g.dim), __ldcg(&g.r[a]));
+    alpha = fmax(alpha, v);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) alpha = fmax(alpha, __shfl_xor_sync(0xffffffffu, alpha, off));
+  if (lane == 0) s_red[warp] = alpha;
+  __syncthreads();
+  alpha = s_red[0];
+  for (int w = 1; w < NW; ++w) alpha = fmax(alpha, s_red[w]);
+  if (alpha < 0.000001) alpha = 0.000001;
+  const double scale = __ddiv_rn(g.rc[b], alpha);
+  for (int c = c0 + tid; c < c1; c += THREADS) {
+    const int a = g.PJ[c];
+    for (int k = 0; k < g.dim; ++k) {
+      const double xv = g.x[(size_t)a * g.dim + k];
+      g.x[(size_t)a * g.dim + k] = __dadd_rn(cb[k], __dmul_rn(scale, __dsub_rn(xv, cb[k])));
+    }
+    g.r[a] = __dmul_rn(scale, __ldcg(&g.r[a]));
+  }
+}
+
+}  // namespace
+
+void level_radii_device(ge_context* ctx, int m, int dim, double* d_x, double* d_r,
+                        const RadiiLevel* lv, const double* d_xc, const double* d_rc) {
+  if (m <= 0) return;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  GE_CUDA(cudaEventCreate(&ev0));
+  GE_CUDA(cudaEventCreate(&ev1));
+  GE_CUDA(cudaEventRecord(ev0, st));
+  GE_CUDA(cudaMemsetAsync(d_r, 0, sizeof(double) * (size_t)m, st));
+  GrowArgs g{};
+  g.dim = dim;
+  g.m_limit = m;
+  g.x = d_x;
+  g.r = d_r;
+  g.class_split = 2048;
+  DevBuf<double> ev_t;
+  DevBuf<int2> ev_ij;
+  DevBuf<int> cnt, off, sums;
+  if (lv == nullptr) {  // base case: all pairs
+    const long long E = (long long)m * (m - 1) / 2;
+    GE_REQUIRE(m <= kRadiiBaseMax, "coarsest level too large for the all-pairs radii step on the device");
+    if (E > 0) {
+      ev_t.alloc(ctx, (size_t)E);
+      ev_ij.alloc(ctx, (size_t)E);
+      k_radii_events_base<<<m, 128, 0, st>>>(m, dim, d_x, ev_t.get(), ev_ij.get());
+      GE_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    g.general = 0;
+    g.nfam = 1;
+    g.ev_t = ev_t.get();
+    g.ev_ij = ev_ij.get();
+    g.E_base = E;
+    g.class_split = -1;  // always the wide kernel
+    k_radii_grow<1024, true><<<1, 1024, 0, st>>>(g);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches++;
+  } else {
+    const int mc = lv->mc;
+    const int nb = (m + kScanBlock - 1) / kScanBlock;
+    cnt.alloc(ctx, (size_t)m);
+    off.alloc(ctx, (size_t)m + 1);
+    sums.alloc(ctx, (size_t)nb + 1);
+    const unsigned wgrid = (unsigned)(((long long)m * 32 + 255) / 256);
+    k_radii_events<false><<<wgrid, 256, 0, st>>>(m, dim, lv->I, lv->J, lv->parent, lv->PJ, d_x,
+                                                 cnt.get(), nullptr, nullptr, nullptr);
+    k_rscan_blocks<<<nb, kScanBlock, 0, st>>>(cnt.get(), m, off.get(), sums.get());
+    k_rscan_sums<<<1, kScanBlock, 0, st>>>(sums.get(), nb);
+    k_rscan_add<<<nb, kScanBlock, 0, st>>>(off.get(), m, sums.get(), nb);
+    GE_CUDA(cudaGetLastError());
+    ctx->launches += 4;
+    int total = 0;  // the number of events sizes the event arrays: one 4-byte round trip per level
+    GE_CUDA(cudaMemcpyAsync(&total, off.get() + m, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GE_CUDA(cudaStreamSynchronize(st));
+    ev_t.alloc(ctx, (size_t)std::max(total, 1));
+    ev_ij.alloc(ctx, (size_t)std::max(total, 1));
+    if (total > 0) {
+      k_radii_events<true><<<wgrid, 256, 0, st>>>(m, dim, lv->I, lv->J, lv->parent, lv->PJ, d_x,
+                                                  nullptr, off.get(), ev_t.get(), ev_ij.get());
+      GE_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    g.general = 1;
+    g.nfam = mc;
+    g.PI = lv->PI;
+    g.PJ = lv->PJ;
+    g.ev_off = off.get();
+    g.ev_t = ev_t.get();
+    g.ev_ij = ev_ij.get();
+    g.xc = d_xc;
+    g.rc = d_rc;
+    if (mc > 0) {
+      k_radii_grow<64, false><<<mc, 64, 0, st>>>(g);
+      k_radii_grow<1024, true><<<mc, 1024, 0, st>>>(g);
+      GE_CUDA(cudaGetLastError());
+      ctx->launches += 2;
+    }
+  }
+  GE_CUDA(cudaEventRecord(ev1, st));
+  GE_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) ctx->radii_ms += ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+}
+
+}  // namespace ge

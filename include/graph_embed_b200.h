@@ -170,6 +170,13 @@ ge_status ge_multilevel_forces(ge_context* ctx, const ge_csr* A, const ge_csr* P
  * coords_Ac (mc x dim) / r_Ac (mc) = the next-coarser level's rescaled centres and radii. */
 ge_status ge_level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,
                          const ge_csr* P_T_c, const double* coords_Ac, const double* r_Ac);
+/* The same step on the device: one CTA per family pops the events in
+ * the reference's order; bit-identical to ge_level_radii.  ge_embed runs this between the levels
+ * on coordinates that never leave the device; this entry point (host buffers in and out) exists
+ * for callers that drive the levels themselves (embedVia) and for the parity tests. */
+ge_status ge_level_radii_device(ge_context* ctx, int m, int dim, double* coords_A, double* r_A,
+                                const ge_csr* A_c, const ge_csr* P_T_c, const double* coords_Ac,
+                                const double* r_Ac);
 /* ---- Galerkin coarse graph -------------------------------------- */
 typedef struct ge_galerkin_stats {
   double device_ms;        /* kernels + the row-length round trip (CUDA events) */
