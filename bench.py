@@ -449,17 +449,35 @@ def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, 
         dt = time.time() - t
         note = "ge_flat_forceatlas(host CSR, host coords, iterations=1) per step"
     else:
-        plan.upload(x)
+        # N > 1: the same public call, ge_flat_forceatlas, on a context that owns all N GPUs
+        # (ge_context_create_multi: one process, NCCL inside the library).  Rank 0 makes the call;
+        # the other ranks' processes hold their GPUs idle behind the barriers.
+        import scipy.sparse as sp
+        dt = 0.0
+        note = ("ge_flat_forceatlas(host CSR, host coords, iterations=1) per step on a %d-GPU context "
+                "(ge_context_create_multi), called from rank 0" % world)
         barrier()
-        h0, d0 = ctx.bytes_moved
-        t = time.time()
-        for _ in range(steps):
-            plan.upload(x)
-            one_step()
-            x = plan.download()
+        if rank == 0:
+            mctx = capi.Context(devices=list(range(world)))
+            Ap = sp.csr_matrix((pin(A.data), pin(A.indices), pin(A.indptr)), shape=A.shape)
+            p1 = capi.flat_params(iterations=1)
+            mctx.flat_forceatlas(Ap, dim, x, p1)  # warm-up (NCCL channels, memory pools)
+            h0, d0 = mctx.bytes_moved
+            t = time.time()
+            for _ in range(steps):
+                mctx.flat_forceatlas(Ap, dim, x, p1, inplace=True)
+            dt = time.time() - t
+            h1, d1 = mctx.bytes_moved
+            mctx.close()
         barrier()
-        dt = time.time() - t
-        note = "flat plan: upload coords, one iteration (pair sums, exchange, step, all-gather), download coords per step"
+        tt = torch.tensor([dt, 0.0, 0.0], dtype=torch.float64, device="cuda")
+        if rank == 0:
+            tt[1], tt[2] = (h1 - h0) / steps, (d1 - d0) / steps
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0].item())
+        return {"value": alg["pairs"] * steps / dt, "unit": "pair-interactions/s", "steps": steps,
+                "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": float(tt[1].item()),
+                "d2h_bytes_per_step": float(tt[2].item()), "api": note, "host_memory": "pinned"}
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libgraphembed_b200.so")
-SOURCES = ["ge_capi.cu", "ge_flat.cu", "ge_flat_sym.cu", "ge_onchip.cu", "ge_multilevel.cu", "ge_galerkin.cu", "ge_radii.cu"]
+SOURCES = ["ge_capi.cu", "ge_flat.cu", "ge_flat_sym.cu", "ge_onchip.cu", "ge_multilevel.cu", "ge_galerkin.cu", "ge_radii.cu", "ge_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 
@@ -51,7 +51,7 @@ def build_library(verbose=False, force=False):
             list(pool.map(subprocess.check_call, jobs))
     if force or _stale(LIB, objs):
         subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB]
-                              + objs + ["-cudart", "static"])
+                              + objs + ["-cudart", "static", "-ldl"])
     return LIB
 
 

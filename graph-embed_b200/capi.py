@@ -72,6 +72,7 @@ SYMBOLS = [
     "ge_flat_plan_create_symmetric", "ge_flat_plan_is_symmetric", "ge_flat_plan_pair_sums",
     "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
     "ge_flat_symmetric_share", "ge_galerkin", "ge_level_radii_device",
+    "ge_context_create_multi", "ge_context_device_count",
 ]
 
 _lib = None
@@ -184,10 +185,19 @@ def level_radii(coords_A, dim, A_c=None, P_T_c=None, coords_Ac=None, r_Ac=None):
 class Context:
     """ge_context: one device + stream.  Raises GeError(GE_ERR_NO_DEVICE) without a B200."""
 
-    def __init__(self, device=-1, stream=None):
+    def __init__(self, device=-1, stream=None, devices=None):
+        """devices=[d0, d1, ...]: one context over several GPUs (ge_context_create_multi)."""
         self.h = C.c_void_p()
-        _check(lib().ge_context_create(int(device), C.c_void_p(stream) if stream else None,
-                                       C.byref(self.h)))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(lib().ge_context_create_multi(len(devices), ids, C.byref(self.h)))
+        else:
+            _check(lib().ge_context_create(int(device), C.c_void_p(stream) if stream else None,
+                                           C.byref(self.h)))
+
+    @property
+    def device_count(self):
+        return int(lib().ge_context_device_count(self.h))
 
     def close(self):
         if self.h:

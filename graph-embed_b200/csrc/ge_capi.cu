@@ -387,6 +387,12 @@ void flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const
     onchip_flat_solve(ctx, A, dim, p, coords, nullptr, false);
     return;
   }
+  // a multi-device context shards the iteration (graphs too small for the symmetric sweep stay on
+  // the context's first device: nothing to share out)
+  if (path == 0 && multi_size(ctx) > 1 && A.rows >= 32768 && std::getenv("GE_REP_SYM") == nullptr) {
+    multi_flat_solve(ctx, A, dim, coords, p);
+    return;
+  }
   std::unique_ptr<FlatSolver> s(make_flat_solver(ctx, A, dim, p, 0, A.rows));
   s->upload_coords(coords);
   int it = 0;
@@ -428,6 +434,8 @@ void flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const
   s->download_coords(coords);
 }
 
+// partition::embed on one device or, with a multi-device context, with the large levels sharded by
+// aggregates (aggregates are independent, include/forceatlas.hpp:340-341).
 struct EmbedRun {
   ge_context* ctx;
   int L, dim;
@@ -436,116 +444,181 @@ struct EmbedRun {
   ge_embed_options opt;
   ge_embed_stats st{};
 
-  // The level graphs are inputs that do not depend on any result: a helper thread uploads the
-  // large ones on the copy stream while the coarsest-level solve (one long kernel that needs no
-  // host attention) occupies the main stream.
-  std::vector<std::unique_ptr<PrefetchedGraph>> pre;
-  std::thread prefetcher;
-  std::string prefetch_error;
-  ge_status prefetch_status = GE_OK;
-  double prefetch_h2d = 0.0;
+  // Per device: the level graphs + slot layouts (inputs that do not depend on any result: a helper
+  // thread uploads the large ones on the device's copy stream while the coarsest-level solve, one
+  // long kernel that needs no host attention, occupies device 0), the coordinates dx[k] (n_k x dim)
+  // and ball radii dr[k] (n_k) of the levels, which never leave the device, and the range of
+  // aggregates [a0[l], a1[l]) the device solves at level l.
+  struct Dev {
+    ge_context* ctx = nullptr;
+    std::vector<std::unique_ptr<PrefetchedGraph>> pre;
+    std::vector<DevBuf<double>> dx, dr;
+    std::vector<int> a0, a1;
+    std::thread prefetcher;
+    std::string error;
+    ge_status status = GE_OK;
+    double prefetch_h2d = 0.0;
+  };
+  std::vector<Dev> devs;
+  std::vector<char> sharded;  // per level
   static constexpr int64_t kPrefetchMinNnz = 1 << 22;  // ~50 MB of CSR: below, the upload is < 2 ms
 
-  void start_prefetch() {
-    pre.resize(L);
-    bool any = false;
-    for (int l = 0; l < L; ++l) any = any || As[l].nnz >= kPrefetchMinNnz;
-    if (!any || std::getenv("GE_NO_PREFETCH")) return;
-    if (!ctx->copy_stream) GE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    prefetcher = std::thread([this] {
-      try {
-        GE_CUDA(cudaSetDevice(ctx->device));
-        ge_context side = *ctx;  // same device and pool, its own stream / staging ring / counters
-        side.stream = ctx->copy_stream;
-        side.stager = ctx->stager2;
-        side.h2d_bytes = 0;
-        for (int l = 0; l < L; ++l) {  // finest first: it is the largest and the last one needed
-          const ge_csr& A = As[l];
-          if (A.nnz < kPrefetchMinNnz) continue;
-          std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
-          g->I.alloc(&side, A.rows + 1);
-          g->J.alloc(&side, (size_t)A.nnz);
-          g->I.upload(&side, A.indptr, A.rows + 1);
-          g->J.upload(&side, A.indices, (size_t)A.nnz);
-          if (A.data != nullptr) {
-            g->Dw.alloc(&side, (size_t)A.nnz);
-            g->Dw.upload(&side, A.data, (size_t)A.nnz);
-          }
-          g->layout = make_level_layout(&side, Ps[l], A.rows);  // slot layout + its device copies
-          GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
-          GE_CUDA(cudaEventRecord(g->ready, side.stream));
-          pre[l] = std::move(g);
-        }
-        ctx->stager2 = side.stager;  // keep the ring for the next call
-        prefetch_h2d = side.h2d_bytes;
-      } catch (const Fail& f) {
-        prefetch_status = f.st;
-        prefetch_error = ge_last_error();
-      } catch (const std::exception& e) {
-        prefetch_status = GE_ERR_INVALID;
-        prefetch_error = e.what();
+  // Levels with at least this many ordered pairs per iteration are shared out over the devices
+  // (cost-balanced contiguous aggregate ranges); smaller ones cost less than the exchange.
+  void plan_ranges() {
+    const int N = multi_size(ctx);
+    devs.resize(N);
+    sharded.assign(std::max(L, 1), 0);
+    for (int d = 0; d < N; ++d) {
+      devs[d].ctx = multi_device(ctx, d);
+      devs[d].pre.resize(L);
+      devs[d].dx.resize(L + 1);
+      devs[d].dr.resize(L + 1);
+      devs[d].a0.assign(L, 0);
+      devs[d].a1.assign(L, 0);
+    }
+    const char* e = std::getenv("GE_SHARD_MIN_MPAIRS");
+    const double min_pairs = 1e6 * (e ? std::atof(e) : 200.0);
+    for (int l = 0; l < L; ++l) {
+      const ge_csr& P = Ps[l];
+      const int m = P.rows;
+      devs[0].a1[l] = m;
+      if (N == 1) continue;
+      std::vector<double> cost((size_t)m + 1, 0.0);
+      double pairs = 0.0;
+      for (int a = 0; a < m; ++a) {
+        const double s = P.indptr[a + 1] - P.indptr[a];
+        double nnz = 0.0;
+        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
+          nnz += As[l].indptr[P.indices[c] + 1] - As[l].indptr[P.indices[c]];
+        pairs += s * (s - 1);
+        cost[a + 1] = cost[a] + s * s + nnz;
       }
-    });
+      if (pairs < min_pairs) continue;
+      sharded[l] = 1;
+      int prev = 0;
+      for (int d = 0; d < N; ++d) {
+        const double target = cost[m] * (d + 1) / N;
+        int cut = d == N - 1 ? m : (int)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
+        cut = std::max(prev, std::min(cut, m));
+        devs[d].a0[l] = prev;
+        devs[d].a1[l] = cut;
+        prev = cut;
+      }
+    }
+  }
+
+  static void upload_graph(ge_context* c, const ge_csr& A, PrefetchedGraph& g) {
+    g.I.alloc(c, A.rows + 1);
+    g.J.alloc(c, (size_t)std::max<int64_t>(A.nnz, 1));
+    g.I.upload(c, A.indptr, A.rows + 1);
+    g.J.upload(c, A.indices, (size_t)A.nnz);
+    if (A.data != nullptr) {
+      g.Dw.alloc(c, (size_t)std::max<int64_t>(A.nnz, 1));
+      g.Dw.upload(c, A.data, (size_t)A.nnz);
+    }
+  }
+
+  void start_prefetch() {
+    if (std::getenv("GE_NO_PREFETCH")) return;
+    for (size_t d = 0; d < devs.size(); ++d) {
+      bool any = false;
+      for (int l = 0; l < L; ++l)
+        any = any || (As[l].nnz >= kPrefetchMinNnz && (d == 0 || devs[d].a1[l] > devs[d].a0[l]));
+      if (!any) continue;
+      Dev* dev = &devs[d];
+      ge_context* c = dev->ctx;
+      GE_CUDA(cudaSetDevice(c->device));
+      if (!c->copy_stream) GE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      dev->prefetcher = std::thread([this, dev, c, d] {
+        try {
+          GE_CUDA(cudaSetDevice(c->device));
+          ge_context side = *c;  // same device and pool, its own stream / staging ring / counters
+          side.stream = c->copy_stream;
+          side.stager = c->stager2;
+          side.h2d_bytes = 0;
+          for (int l = 0; l < L; ++l) {  // finest first: it is the largest and the last one needed
+            const ge_csr& A = As[l];
+            if (A.nnz < kPrefetchMinNnz) continue;
+            if (d != 0 && dev->a1[l] <= dev->a0[l]) continue;
+            std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
+            upload_graph(&side, A, *g);
+            g->layout = make_level_layout(&side, Ps[l], A.rows, dev->a0[l], dev->a1[l], d == 0);
+            GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
+            GE_CUDA(cudaEventRecord(g->ready, side.stream));
+            dev->pre[l] = std::move(g);
+          }
+          c->stager2 = side.stager;  // keep the ring for the next call
+          dev->prefetch_h2d = side.h2d_bytes;
+        } catch (const Fail& f) {
+          dev->status = f.st;
+          dev->error = ge_last_error();
+        } catch (const std::exception& e) {
+          dev->status = GE_ERR_INVALID;
+          dev->error = e.what();
+        }
+      });
+    }
+    GE_CUDA(cudaSetDevice(ctx->device));
   }
   void join_prefetch() {
-    if (!prefetcher.joinable()) return;
-    prefetcher.join();
-    ctx->h2d_bytes += prefetch_h2d;
-    prefetch_h2d = 0.0;
-    if (prefetch_status != GE_OK) {
-      set_error("level-graph prefetch: " + prefetch_error);
-      throw Fail{prefetch_status};
+    for (auto& dev : devs) {
+      if (!dev.prefetcher.joinable()) continue;
+      dev.prefetcher.join();
+      ctx->h2d_bytes += dev.prefetch_h2d;
+      dev.prefetch_h2d = 0.0;
     }
+    for (auto& dev : devs)
+      if (dev.status != GE_OK) {
+        set_error("level-graph prefetch: " + dev.error);
+        throw Fail{dev.status};
+      }
   }
   ~EmbedRun() {
-    if (prefetcher.joinable()) prefetcher.join();
-    dx.clear();
-    dr.clear();
-    // the prefetched buffers were allocated on the copy stream: nothing on the main stream may
-    // still read them when they are returned to the pool
-    if (!pre.empty()) cudaStreamSynchronize(ctx->stream);
+    for (auto& dev : devs)
+      if (dev.prefetcher.joinable()) dev.prefetcher.join();
+    for (auto& dev : devs) {
+      cudaSetDevice(dev.ctx->device);
+      dev.dx.clear();
+      dev.dr.clear();
+      // the prefetched buffers were allocated on the copy stream: nothing on the main stream may
+      // still read them when they are returned to the pool
+      cudaStreamSynchronize(dev.ctx->stream);
+      dev.pre.clear();
+    }
+    cudaSetDevice(ctx->device);
   }
 
-  // The level graph + slot layout on the device: uploaded ahead of time by the prefetcher (large
-  // levels) or here, on the main stream, when the level is first needed.
-  const PrefetchedGraph* graph(int l) {
-    if (pre.empty()) pre.resize(L);
-    if (pre[l]) return pre[l].get();
+  // The level graph + slot layout on device d: uploaded ahead of time by the prefetcher (large
+  // levels) or here, on the device's main stream, when the level is first needed.
+  const PrefetchedGraph* graph(int d, int l) {
+    Dev& dev = devs[d];
+    if (dev.pre[l]) return dev.pre[l].get();
     const ge_csr& A = As[l];
     std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
-    g->I.alloc(ctx, A.rows + 1);
-    g->J.alloc(ctx, (size_t)std::max<int64_t>(A.nnz, 1));
-    g->I.upload(ctx, A.indptr, A.rows + 1);
-    g->J.upload(ctx, A.indices, (size_t)A.nnz);
-    if (A.data != nullptr) {
-      g->Dw.alloc(ctx, (size_t)std::max<int64_t>(A.nnz, 1));
-      g->Dw.upload(ctx, A.data, (size_t)A.nnz);
-    }
-    g->layout = make_level_layout(ctx, Ps[l], A.rows);
+    upload_graph(dev.ctx, A, *g);
+    g->layout = make_level_layout(dev.ctx, Ps[l], A.rows, dev.a0[l], dev.a1[l], d == 0);
     GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
-    GE_CUDA(cudaEventRecord(g->ready, ctx->stream));
-    pre[l] = std::move(g);
-    return pre[l].get();
+    GE_CUDA(cudaEventRecord(g->ready, dev.ctx->stream));
+    dev.pre[l] = std::move(g);
+    return dev.pre[l].get();
   }
 
-  // Coordinates (dx[k]: n_k x dim) and ball radii (dr[k]: n_k) of every level stay on the device;
-  // only the finest level's coordinates (and, on request, level 1's radii / rescaled coordinates,
-  // the out-parameters of embedMultilevel) are copied back.
-  std::vector<DevBuf<double>> dx, dr;
-
-  // src/embed.cpp:615-778 for the vertices of level k = l + 1.
+  // src/embed.cpp:615-778 for the vertices of level k = l + 1, on device 0.
   void radii(int k) {
+    Dev& d0 = devs[0];
     const int m = As[k].rows;
-    dr[k].alloc(ctx, (size_t)std::max(m, 1));
+    d0.dr[k].alloc(ctx, (size_t)std::max(m, 1));
     const bool base = k == L;
     const bool on_host = std::getenv("GE_HOST_RADII") != nullptr || (base && m > kRadiiBaseMax);
     if (!on_host) {
       if (base) {
-        level_radii_device(ctx, m, dim, dx[k].get(), dr[k].get(), nullptr, nullptr, nullptr);
+        level_radii_device(ctx, m, dim, d0.dx[k].get(), d0.dr[k].get(), nullptr, nullptr, nullptr);
       } else {
-        GE_CUDA(cudaStreamWaitEvent(ctx->stream, graph(k)->ready, 0));
-        const RadiiLevel lv = radii_level_of(*graph(k), As[k + 1].rows);
-        level_radii_device(ctx, m, dim, dx[k].get(), dr[k].get(), &lv, dx[k + 1].get(), dr[k + 1].get());
+        GE_CUDA(cudaStreamWaitEvent(ctx->stream, graph(0, k)->ready, 0));
+        const RadiiLevel lv = radii_level_of(*graph(0, k), As[k + 1].rows);
+        level_radii_device(ctx, m, dim, d0.dx[k].get(), d0.dr[k].get(), &lv, d0.dx[k + 1].get(),
+                           d0.dr[k + 1].get());
       }
       return;
     }
@@ -553,27 +626,44 @@ struct EmbedRun {
     // coarsest level too large for the device's event arrays)
     const double t0 = now_ms();
     std::vector<double> x((size_t)m * dim), r(m, 0.0), xc, rc;
-    dx[k].download(ctx, x.data(), x.size());
+    d0.dx[k].download(ctx, x.data(), x.size());
     if (!base) {
       const int mc = As[k + 1].rows;
       xc.resize((size_t)mc * dim);
       rc.resize(mc);
-      dx[k + 1].download(ctx, xc.data(), xc.size());
-      dr[k + 1].download(ctx, rc.data(), rc.size());
+      d0.dx[k + 1].download(ctx, xc.data(), xc.size());
+      d0.dr[k + 1].download(ctx, rc.data(), rc.size());
     }
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
     if (base) level_radii(m, dim, x.data(), r.data(), nullptr, nullptr, nullptr, nullptr);
     else level_radii(m, dim, x.data(), r.data(), &As[k], &Ps[k], xc.data(), rc.data());
-    dx[k].upload(ctx, x.data(), x.size());
-    dr[k].upload(ctx, r.data(), r.size());
+    d0.dx[k].upload(ctx, x.data(), x.size());
+    d0.dr[k].upload(ctx, r.data(), r.size());
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
     st.host_radii_ms += now_ms() - t0;
   }
 
+  // One level on one device (its range of aggregates).  Runs on the calling thread.
+  void solve_level(int d, int l, const double* init, double* host_out, double* pairs) {
+    Dev& dev = devs[d];
+    ge_params p;
+    ge_params_default_multilevel(&p);
+    p.iterations = opt.level_iterations;  // :793
+    p.precision = opt.precision;
+    p.seed = opt.seed;
+    LevelIO io;
+    io.d_coords_A = dev.dx[l + 1].get();
+    io.d_r_A = dev.dr[l + 1].get();
+    io.keep_out = (l > 0 || sharded[l]) ? &dev.dx[l] : nullptr;
+    io.download = host_out != nullptr;
+    multilevel_solve(dev.ctx, As[l], Ps[l], nullptr, nullptr, nullptr, init, host_out, dim, p, false,
+                     pairs, dev.a0[l], dev.a1[l], graph(d, l), &io);
+  }
+
   // embedMultilevel, src/embed.cpp:576-796, unrolled from the coarsest level up.
   void run(double* coords_out, double* r_A_out, double* coords_A_out) {
-    dx.resize(L + 1);
-    dr.resize(L + 1);
+    Dev& d0 = devs[0];
+    const int N = (int)devs.size();
     {  // :582-587 base: forceAtlas with its defaults on the coarsest graph
       const ge_csr& A = As[L];
       const int n = A.rows;
@@ -589,11 +679,11 @@ struct EmbedRun {
         flat_solve(ctx, A, dim, coords.data(), p, 0);
         std::memcpy(coords_out, coords.data(), coords.size() * sizeof(double));
       } else if (n >= 1 && n <= onchip_threshold()) {
-        onchip_flat_solve(ctx, A, dim, p, coords.data(), nullptr, false, &dx[L]);
+        onchip_flat_solve(ctx, A, dim, p, coords.data(), nullptr, false, &d0.dx[L]);
       } else {
         flat_solve(ctx, A, dim, coords.data(), p, 0);
-        dx[L].alloc(ctx, (size_t)std::max(n, 1) * dim);
-        dx[L].upload(ctx, coords.data(), coords.size());
+        d0.dx[L].alloc(ctx, (size_t)std::max(n, 1) * dim);
+        d0.dx[L].upload(ctx, coords.data(), coords.size());
       }
       st.coarse_ms += now_ms() - t0;
       join_prefetch();  // normally long finished: the solve above takes 0.1-0.2 s
@@ -603,13 +693,16 @@ struct EmbedRun {
     for (int l = L - 1; l >= 0; --l) {
       const ge_csr& A = As[l];
       const ge_csr& P = Ps[l];
-      const int n = A.rows;
+      const int n = A.rows, m = P.rows;
       if (opt.verbose) std::printf("embeding layer %d\n", l + opt.first_layer);
       radii(l + 1);
-      if (l + 2 <= L) {  // the grand-parent level is not needed any more
-        dx[l + 2].release();
-        dr[l + 2].release();
+      for (auto& dev : devs) {  // the grand-parent level is not needed any more
+        if (l + 2 > L) break;
+        GE_CUDA(cudaSetDevice(dev.ctx->device));
+        dev.dx[l + 2].release();
+        dev.dr[l + 2].release();
       }
+      GE_CUDA(cudaSetDevice(ctx->device));
       // Initial local coordinates: with a fixed seed, the reference's own stream in its draw order
       // (forceatlas.hpp:341, 356-358); with seed 0 (the reference's std::random_device mode, where
       // any stream is as good as another) they are drawn on the device.
@@ -618,29 +711,71 @@ struct EmbedRun {
         init.resize((size_t)n * dim);
         level_init_stream(opt.seed, P, dim, init.data());
       }
-      ge_params p;
-      ge_params_default_multilevel(&p);
-      p.iterations = opt.level_iterations;  // :793
-      p.precision = opt.precision;
-      p.seed = opt.seed;
-      LevelIO io;
-      io.d_coords_A = dx[l + 1].get();
-      io.d_r_A = dr[l + 1].get();
-      io.keep_out = l > 0 ? &dx[l] : nullptr;
-      io.download = l == 0;  // the finest level goes straight into the caller's buffer
+      const double* init_p = init.empty() ? nullptr : init.data();
       const double t1 = now_ms();
       double pairs = 0.0;
-      multilevel_solve(ctx, A, P, nullptr, nullptr, nullptr, init.empty() ? nullptr : init.data(),
-                       l == 0 ? coords_out : nullptr, dim, p, false, &pairs, 0, -1, graph(l), &io);
+      if (!sharded[l]) {
+        solve_level(0, l, init_p, l == 0 ? coords_out : nullptr, &pairs);
+      } else {
+        // parent centres and radii to every device, each device its aggregates, then one sum over
+        // the devices (rows of foreign aggregates are exact zeros: x + 0 is exact)
+        std::vector<double*> bx(N), br(N), bo(N);
+        for (int d = 0; d < N; ++d) {
+          Dev& dev = devs[d];
+          GE_CUDA(cudaSetDevice(dev.ctx->device));
+          if (d > 0) {
+            dev.dx[l + 1].alloc(dev.ctx, (size_t)std::max(m, 1) * dim);
+            dev.dr[l + 1].alloc(dev.ctx, (size_t)std::max(m, 1));
+          }
+          bx[d] = dev.dx[l + 1].get();
+          br[d] = dev.dr[l + 1].get();
+        }
+        multi_broadcast_f64(ctx, bx, (size_t)m * dim, 0);
+        multi_broadcast_f64(ctx, br, (size_t)m, 0);
+        std::vector<std::thread> pool;
+        std::vector<double> dpairs(N, 0.0);
+        std::vector<ge_status> status(N, GE_OK);
+        std::vector<std::string> errors(N);
+        for (int d = 0; d < N; ++d)
+          pool.emplace_back([&, d] {
+            try {
+              GE_CUDA(cudaSetDevice(devs[d].ctx->device));
+              solve_level(d, l, init_p, nullptr, &dpairs[d]);
+            } catch (const Fail& f) {
+              status[d] = f.st;
+              errors[d] = ge_last_error();
+            } catch (const std::exception& e) {
+              status[d] = GE_ERR_INVALID;
+              errors[d] = e.what();
+            }
+          });
+        for (auto& t : pool) t.join();
+        for (int d = 0; d < N; ++d)
+          if (status[d] != GE_OK) {
+            set_error("device " + std::to_string(devs[d].ctx->device) + ": " + errors[d]);
+            throw Fail{status[d]};
+          }
+        for (int d = 0; d < N; ++d) {
+          pairs += dpairs[d];
+          bo[d] = devs[d].dx[l].get();
+        }
+        multi_allreduce_sum_f64(ctx, bo, (size_t)n * dim);
+        multi_sync(ctx);
+        if (l == 0) {
+          d0.dx[0].download(ctx, coords_out, (size_t)n * dim);
+          GE_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+      }
       st.levels_ms += now_ms() - t1;
-      st.pair_interactions += pairs * p.iterations;
-      st.edge_visits += double(A.nnz) * p.iterations;
+      st.pair_interactions += pairs * opt.level_iterations;
+      st.edge_visits += double(A.nnz) * opt.level_iterations;
     }
     if (L > 0) {  // what embedMultilevel leaves in its r_A / coords_A out-parameters
-      if (r_A_out) dr[1].download(ctx, r_A_out, (size_t)As[1].rows);
-      if (coords_A_out) dx[1].download(ctx, coords_A_out, (size_t)As[1].rows * dim);
+      if (r_A_out) d0.dr[1].download(ctx, r_A_out, (size_t)As[1].rows);
+      if (coords_A_out) d0.dx[1].download(ctx, coords_A_out, (size_t)As[1].rows * dim);
       if (r_A_out || coords_A_out) GE_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    multi_collect_counters(ctx);
   }
 };
 
@@ -745,8 +880,40 @@ ge_status ge_context_create(int device, void* cuda_stream, ge_context** out) {
   });
 }
 
+ge_status ge_context_create_multi(int ndev, const int* devices, ge_context** out) {
+  ge_context* ctx = nullptr;
+  const ge_status st = guarded([&] {
+    GE_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    GE_REQUIRE(ndev >= 1 && ndev <= 64, "bad device count");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      set_error("no usable CUDA device (this library has no CPU fallback)");
+      throw Fail{GE_ERR_NO_DEVICE};
+    }
+    GE_REQUIRE(ndev <= count, "more devices requested than the box has");
+    const ge_status s0 = ge_context_create(devices ? devices[0] : 0, nullptr, &ctx);
+    if (s0 != GE_OK) throw Fail{s0};
+    if (ndev > 1) multi_attach(ctx, ndev, devices);
+    *out = ctx;
+  });
+  if (st != GE_OK && ctx != nullptr) {
+    const std::string keep = g_error;
+    ge_context_destroy(ctx);
+    g_error = keep;
+  }
+  return st;
+}
+int32_t ge_context_device_count(const ge_context* ctx) { return ctx ? multi_size(ctx) : 0; }
+
 void ge_context_destroy(ge_context* ctx) {
   if (!ctx) return;
+  if (ctx->multi) {
+    multi_destroy(ctx->multi);
+    ctx->multi = nullptr;
+    cudaSetDevice(ctx->device);
+  }
   if (ctx->stager) {
     cudaStreamSynchronize(ctx->stream);
     delete ctx->stager;
@@ -848,6 +1015,7 @@ ge_status ge_embed(ge_context* ctx, int n_levels, const ge_csr* As, const ge_csr
     ctx->grid_tier_ms = 0;
     ctx->radii_ms = 0;
     const double t0 = now_ms();
+    run.plan_ranges();
     run.start_prefetch();
     run.run(coords_out, r_A_out, coords_A_out);
     run.st.total_ms = now_ms() - t0;

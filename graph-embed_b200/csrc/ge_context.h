@@ -12,7 +12,8 @@
 #include "ge_common.cuh"
 
 namespace ge {
-struct Stager;  // pinned staging ring for large host->device copies (ge_capi.cu)
+struct Stager;      // pinned staging ring for large host->device copies (ge_capi.cu)
+struct MultiState;  // sub-contexts of the other devices + NCCL communicator (ge_multi.cu)
 }
 
 struct ge_context {
@@ -32,6 +33,7 @@ struct ge_context {
   // over the levels of one ge_embed call (CUDA events on the context stream)
   double grid_tier_ms = 0;
   double radii_ms = 0;  // device time of the ball-radius / rescale kernels
+  ge::MultiState* multi = nullptr;  // ge_context_create_multi: this context drives several devices
 };
 
 namespace ge {
@@ -146,7 +148,8 @@ void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_param
 // A level graph already on the device (uploaded ahead of time on another stream); `ready` is
 // recorded after the last copy.
 struct LevelLayout;  // slot layout of a level (ge_multilevel.cu): depends on P_T only
-LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n);
+LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n, int agg_begin = 0,
+                               int agg_end = -1, bool members = true);
 void free_level_layout(LevelLayout* layout);
 struct PrefetchedGraph {
   DevBuf<int> I, J;
@@ -197,6 +200,18 @@ RadiiLevel radii_level_of(const PrefetchedGraph& g, int mc);
 // ---- ge_galerkin.cu ----------------------------------------------------------------------------
 int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, int32_t* c_indptr,
                  int32_t* c_indices, double* c_data, int64_t capacity, ge_galerkin_stats* stats);
+
+// ---- ge_multi.cu ---------------------------------------------------------------------------------
+void multi_attach(ge_context* ctx, int ndev, const int* devices);
+void multi_destroy(MultiState* m);
+int multi_size(const ge_context* ctx);
+void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const ge_params& p);
+ge_context* multi_device(ge_context* ctx, int r);  // sub-context of device r (0: ctx itself)
+// bufs[r]: a buffer of `count` doubles on device r.  Enqueued on the devices' streams.
+void multi_broadcast_f64(ge_context* ctx, const std::vector<double*>& bufs, size_t count, int root);
+void multi_allreduce_sum_f64(ge_context* ctx, const std::vector<double*>& bufs, size_t count);
+void multi_sync(ge_context* ctx);                // every device's stream
+void multi_collect_counters(ge_context* ctx);    // fold the sub-contexts' counters into ctx
 
 // ---- ge_capi.cu (host-side level driver) -------------------------------------------------------
 void level_radii(int m, int dim, double* coords_A, double* r_A, const ge_csr* A_c,

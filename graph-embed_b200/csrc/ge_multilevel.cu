@@ -258,12 +258,12 @@ struct LevelLayout {
   double pairs = 0.0;
   DevBuf<int> d_vA, d_vtx, d_slot_of, d_agg_base, d_agg_of_slot;
   DevBuf<int> d_PI, d_PJ;  // the aggregation's CSR (member lists): the families of the radii step
-  int n = 0, m = 0;
+  int n = 0, m = 0, agg_begin = 0, agg_end = 0;
 };
 
 namespace {
 void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* v_A, bool forces_only,
-                        int agg_begin, int agg_end, LevelLayout& L_) {
+                        int agg_begin, int agg_end, LevelLayout& L_, bool members = false) {
   const int m = P.rows;
   const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
   std::vector<int4>& segs = L_.segs;
@@ -358,7 +358,7 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   L_.d_slot_of.upload(ctx, slot_of.data(), n);
   L_.d_agg_base.upload(ctx, agg_base.data(), m);
   L_.d_agg_of_slot.upload(ctx, agg_of_slot.data(), (size_t)ld);
-  if (!forces_only && agg_begin == 0 && agg_end == m) {
+  if (members) {
     L_.d_PI.alloc(ctx, (size_t)m + 1);
     L_.d_PJ.alloc(ctx, (size_t)std::max(n, 1));
     L_.d_PI.upload(ctx, P.indptr, (size_t)m + 1);
@@ -366,6 +366,8 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   }
   L_.n = n;
   L_.m = m;
+  L_.agg_begin = agg_begin;
+  L_.agg_end = agg_end;
   // (copies from pageable memory have left the host arrays when cudaMemcpyAsync returns)
 }
 
@@ -392,6 +394,8 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   // ---- slot layout (host + its device copies): prepared ahead of time or built here ----------
   LevelLayout own_layout;
   const LevelLayout* lay = (pre != nullptr && pre->layout != nullptr) ? pre->layout : nullptr;
+  if (lay != nullptr)
+    GE_REQUIRE(lay->agg_begin == agg_begin && lay->agg_end == agg_end, "prepared layout covers another aggregate range");
   if (lay == nullptr) {
     build_level_layout(ctx, P, n, v_A, forces_only, agg_begin, agg_end, own_layout);
     lay = &own_layout;
@@ -656,9 +660,11 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 
 }  // namespace
 
-LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n) {
+LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n, int agg_begin, int agg_end,
+                               bool members) {
+  if (agg_end < 0) agg_end = P_T.rows;
   std::unique_ptr<LevelLayout> L(new LevelLayout);
-  build_level_layout(ctx, P_T, n, nullptr, false, 0, P_T.rows, *L);
+  build_level_layout(ctx, P_T, n, nullptr, false, agg_begin, agg_end, *L, members);
   return L.release();
 }
 void free_level_layout(LevelLayout* layout) { delete layout; }

@@ -677,7 +677,7 @@ void launch_onchip_cta(ge_context* ctx, const OnchipArgs<T>& a, int ntasks, int 
   const size_t smem = cta_smem<T>(dim, max_size, lanes, big);
   const void* fn = dim == 2 ? (ml ? cta_kernel<T, 2, true>(lanes, big, ga) : cta_kernel<T, 2, false>(lanes, big, ga))
                             : (ml ? cta_kernel<T, 3, true>(lanes, big, ga) : cta_kernel<T, 3, false>(lanes, big, ga));
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default limit too)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&a};
   GE_CUDA(cudaLaunchKernel(fn, dim3(ntasks), dim3(threads), args, smem, ctx->stream));
@@ -731,7 +731,7 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   const void* fn = dim == 2 ? (ga ? cluster_kernel<T, 2, true>(L) : cluster_kernel<T, 2, false>(L))
                             : (ga ? cluster_kernel<T, 3, true>(L) : cluster_kernel<T, 3, false>(L));
   const size_t smem = cta_smem<T>(dim, n, L, false);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default limit too)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(csize);

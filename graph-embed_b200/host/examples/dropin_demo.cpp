@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
+#include <string>
 
 #include "embed.hpp"
 
@@ -35,7 +36,33 @@ SparseMatrix blocks(int nx, int ny) {
 
 }  // namespace
 
+// `--gpus N`: partition::forceAtlas (include/forceatlas.hpp:89-305) on a 200 x 200 grid, sharded
+// over N GPUs of this box by the library (one process, NCCL inside the context).
+int flat_on_gpus(int gpus, int dimension) {
+  ge_b200::options().gpus = gpus;
+  ge_b200::options().seed = 7;
+  const SparseMatrix A = grid(200, 200);
+  std::vector<std::vector<double>> coords(0);
+  linalgcpp::Timer timer(linalgcpp::Timer::Start::True);
+  partition::forceAtlas(A, dimension, coords, 20);
+  timer.Click();
+  std::cout << "forceAtlas: " << A.Rows() << " vertices, 20 iterations on "
+            << ge_context_device_count(ge_b200::default_context()) << " GPU(s) in " << timer[0] << "s"
+            << std::endl;
+  double sum = 0.0;
+  for (size_t i = 0; i < coords.size(); i++)
+    for (int k = 0; k < dimension; k++) {
+      if (std::isnan(coords[i][k])) return 1;
+      sum += coords[i][k];
+    }
+  std::cout.precision(17);
+  std::cout << "checksum " << sum << std::endl;
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  for (int a = 1; a + 1 < argc; ++a)
+    if (std::string(argv[a]) == "--gpus") return flat_on_gpus(std::atoi(argv[a + 1]), 2);
   int nx = argc > 1 ? std::atoi(argv[1]) : 64, ny = nx;
   const int dimension = argc > 2 ? std::atoi(argv[2]) : 2;
   std::vector<SparseMatrix> As = {grid(nx, ny)}, hierarchy;

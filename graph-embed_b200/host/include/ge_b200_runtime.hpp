@@ -2,6 +2,7 @@
 #ifndef GE_B200_RUNTIME_HPP
 #define GE_B200_RUNTIME_HPP
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -11,14 +12,34 @@
 
 namespace ge_b200 {
 
-// Process-wide context on the current CUDA device (the reference keeps no state either; the
-// context only owns a stream and the device memory pool).
+// Knobs the reference does not have (precision, seed, GPU count); change before the first call
+// into the library (the GPU count is read once, when the process-wide context is created).
+struct Options {
+  int precision = GE_F64;
+  unsigned seed = 0;   // 0: std::random_device like the reference
+  bool verbose = true; // print the reference's "embedding layer N" progress lines
+  int gpus = 0;        // 0: the environment variable GE_GPUS, else 1.  > 1: partition::forceAtlas on
+                       // graphs of >= 32768 vertices is sharded over that many GPUs of the box
+};
+inline Options& options() {
+  static Options o;
+  return o;
+}
+
+// Process-wide context (the reference keeps no state either; the context only owns streams, the
+// device memory pools and, with several GPUs, the NCCL communicator).
 inline ge_context* default_context() {
   struct Holder {
     ge_context* ctx = nullptr;
     Holder() {
-      if (ge_context_create(-1, nullptr, &ctx) != GE_OK)
-        throw std::runtime_error(std::string("graph-embed_b200: ") + ge_last_error());
+      int gpus = options().gpus;
+      if (gpus <= 0) {
+        const char* e = std::getenv("GE_GPUS");
+        gpus = e ? std::atoi(e) : 1;
+      }
+      const ge_status st = gpus > 1 ? ge_context_create_multi(gpus, nullptr, &ctx)
+                                    : ge_context_create(-1, nullptr, &ctx);
+      if (st != GE_OK) throw std::runtime_error(std::string("graph-embed_b200: ") + ge_last_error());
     }
     ~Holder() { ge_context_destroy(ctx); }
   };
@@ -70,17 +91,6 @@ inline SparseMatrix galerkin(const SparseMatrix& A, const SparseMatrix& P_T) {
   indices.resize(static_cast<size_t>(nnz));
   data.resize(static_cast<size_t>(nnz));
   return SparseMatrix(std::move(indptr), std::move(indices), std::move(data), P_T.Rows(), P_T.Rows());
-}
-
-// Knobs the reference does not have (precision, seed); change before calling partition::embed.
-struct Options {
-  int precision = GE_F64;
-  unsigned seed = 0;   // 0: std::random_device like the reference
-  bool verbose = true; // print the reference's "embedding layer N" progress lines
-};
-inline Options& options() {
-  static Options o;
-  return o;
 }
 
 }  // namespace ge_b200

@@ -103,6 +103,17 @@ void ge_embed_options_default(ge_embed_options* o);
 /* ---- context ---------------------------------------------------------------------------- */
 /* device < 0 selects the current device.  stream == NULL: the context creates its own. */
 ge_status ge_context_create(int device, void* cuda_stream, ge_context** out);
+/* One process, `ndev` GPUs of one box (device ordinals devices[0..ndev), or 0..ndev-1 when devices
+ * is NULL): the context owns a stream and memory pool per device and an NCCL communicator over
+ * them (NCCL is bound at run time; GE_ERR_UNSUPPORTED if libnccl.so.2 cannot be loaded).  On such a
+ * context ge_flat_forceatlas -- hence partition::forceAtlas through the C++ shim -- shards the
+ * iteration: every device evaluates 1/ndev of the unordered pairs, the pair sums are
+ * reduce-scattered, each device steps its row block and the new positions are all-gathered
+ * (include/forceatlas.hpp:146-270; no all-reduce, the global swing sums are dead code).  Graphs
+ * below 32768 vertices and the other entry points run on devices[0].  ndev must divide the row
+ * count padded to 256 (1, 2, 4, 8 always do). */
+ge_status ge_context_create_multi(int ndev, const int* devices, ge_context** out);
+int32_t ge_context_device_count(const ge_context* ctx);
 void ge_context_destroy(ge_context* ctx);
 /* Kernels launched by this context since creation (the library counts its own launches). */
 int64_t ge_context_launch_count(const ge_context* ctx);

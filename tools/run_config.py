@@ -3,6 +3,7 @@
 --ref      use the hierarchy of the REFERENCE's partitioner cached under tests/golden/refhier_*.npz
            (config3: R-MAT-20; config5: Delaunay of n_points = 1000000 or 4000000) instead of the
            stand-in generator graphs.coarsen
+--gpus=N   one context over N GPUs of the box (large levels sharded by aggregates)
 --cpu-ref  also time the compiled reference's embed() (oracle/_ref, all host threads) on the same
            hierarchy -- minutes of CPU
 Prints one JSON line: hierarchy shape, embed() wall time, per-phase times, properties."""
@@ -54,7 +55,12 @@ def main():
         As, Ps = graphs.coarsen(A, cf, min_coarse=64)
         t_coarsen = time.time() - t
     stats = graphs.level_stats(As, Ps)
-    ctx = capi.Context(0)
+    gpus = 1
+    for f in flags:
+        if f.startswith("--gpus="):
+            gpus = int(f.split("=")[1])
+    # --gpus=N: one context over N GPUs (ge_context_create_multi); large levels are sharded by aggregates
+    ctx = capi.Context(0) if gpus == 1 else capi.Context(devices=list(range(gpus)))
     ctx.embed(As[-2:], Ps[-1:], dim, seed=1, coarse_iterations=100)  # warm-up (context, pool)
     walls = []
     for rep in range(2):   # seed 0: the reference's own (std::random_device) mode
@@ -93,7 +99,7 @@ def main():
             os.dup2(fd, 1)
             os.close(fd)
         cpu = {"embed_wall_s": secs, "threads": threads, "kind": "reference (oracle/_ref, -O3, OpenMP)"}
-    out = {"config": name, "hierarchy": ("reference partitioner (src/partitioner.cpp:1550-1893), cached"
+    out = {"config": name, "gpus": gpus, "hierarchy": ("reference partitioner (src/partitioner.cpp:1550-1893), cached"
                                          if use_ref else "stand-in generator graphs.coarsen"),
            "cpu_reference": cpu, "grid_tier_ms": st["grid_tier_ms"], "device_radii_ms": st["device_radii_ms"],
            "grid_tier_share_of_levels": st["grid_tier_ms"] / max(st["levels_ms"], 1e-9),
