@@ -456,6 +456,9 @@ def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, 
         dt = 0.0
         note = ("ge_flat_forceatlas(host CSR, host coords, iterations=1) per step on a %d-GPU context "
                 "(ge_context_create_multi), called from rank 0" % world)
+        # the other ranks wait on a CPU (gloo) barrier: an NCCL barrier would park a spinning kernel
+        # on their GPUs, which rank 0's context is about to use
+        cpu_group = dist.new_group(backend="gloo")
         barrier()
         if rank == 0:
             mctx = capi.Context(devices=list(range(world)))
@@ -469,7 +472,7 @@ def bench_e2e(args, torch, dist, capi, sharding, ctx, plan, A, x0, world, rank, 
             dt = time.time() - t
             h1, d1 = mctx.bytes_moved
             mctx.close()
-        barrier()
+        dist.barrier(group=cpu_group)
         tt = torch.tensor([dt, 0.0, 0.0], dtype=torch.float64, device="cuda")
         if rank == 0:
             tt[1], tt[2] = (h1 - h0) / steps, (d1 - d0) / steps

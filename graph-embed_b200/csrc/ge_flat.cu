@@ -12,6 +12,7 @@
 // Device layout: coordinates, masses and forces are SoA [dim][ld] (ld = n padded to the column
 // tile) so every access is coalesced and each array of a column tile is one contiguous bulk copy.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -759,11 +760,14 @@ template <typename T, int D, int G, bool GA, int CAP, int MINB>
 void launch_staged_c(ge_context* ctx, const StepArgs<T>& a) {
   const size_t smem = 2 * CAP * (sizeof(T) + sizeof(int)) + 2 * sizeof(uint64_t);
   auto fn = k_attract_step_staged<T, D, G, GA, CAP, MINB>;
-  static int occ = 0;  // per instantiation
+  static std::atomic<int> occ_dev[64];  // per instantiation and device (function attributes are per device)
+  const int di = ctx->device & 63;
+  int occ = occ_dev[di].load();
   if (occ == 0) {
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, smem));
     GE_REQUIRE(occ > 0, "staged attraction kernel does not fit on an SM");
+    occ_dev[di].store(occ);
   }
   const int rpc = 256 / G;
   const int nchunks = (a.nrows + rpc - 1) / rpc;

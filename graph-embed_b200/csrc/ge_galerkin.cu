@@ -518,12 +518,9 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   g.gkeys = d_gkeys.get();
   g.gvals = d_gvals.get();
   g.bigoff = d_bigoff.get();
-  static bool attr_set = false;
-  if (!attr_set) {
-    GE_CUDA(cudaFuncSetAttribute(k_gal_segment<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kGalSmemMax * 16));
-    attr_set = true;
-  }
+  // (function attributes are per device: set on every call, it costs microseconds)
+  GE_CUDA(cudaFuncSetAttribute(k_gal_segment<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kGalSmemMax * 16));
   for (int k = 0; k < kClasses; ++k) {
     const int cnt = class_begin[k + 1] - class_begin[k];
     if (cnt == 0) continue;

@@ -177,6 +177,15 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
   const int64_t ld = round_up(std::max(n, 1), 256);
   GE_REQUIRE(ld % N == 0, "device count does not divide the padded row count");
   const int64_t R = ld / N;
+  const bool verbose = std::getenv("GE_VERBOSE") != nullptr;
+  double t_mark = now_ms();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    multi_sync(ctx);
+    const double t = now_ms();
+    std::fprintf(stderr, "[ge] multi flat n=%d N=%d %-14s %8.3f ms\n", n, N, what, t - t_mark);
+    t_mark = t;
+  };
   std::vector<std::unique_ptr<FlatSolver>> solver(N);
   std::vector<ge_status> status(N, GE_OK);
   std::vector<std::string> errors(N);
@@ -203,6 +212,7 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
         throw Fail{status[r]};
       }
   }
+  lap("plans + upload");
   const int dt = solver[0]->elem_size() == 8 ? kNcclFloat64 : kNcclFloat32;
   const size_t w = (size_t)solver[0]->elem_size();
   for (int it = 0; it < p.iterations; ++it) {
@@ -232,6 +242,7 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
     GE_NCCL(M.nccl, M.nccl.GroupEnd());
     for (int r = 0; r < N; ++r) solver[r]->swap();
   }
+  lap("iterations");
   for (int r = 1; r < N; ++r) {
     GE_CUDA(cudaSetDevice(M.dev[r]->device));
     GE_CUDA(cudaStreamSynchronize(M.dev[r]->stream));
@@ -243,11 +254,13 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
   GE_CUDA(cudaSetDevice(ctx->device));
   if (p.normalize) solver[0]->normalize();  // every device holds all positions after the all-gather
   solver[0]->download_coords(coords);
+  lap("download");
   for (int r = N - 1; r >= 0; --r) {  // free each plan's memory on its own device
     GE_CUDA(cudaSetDevice(M.dev[r]->device));
     solver[r].reset();
   }
   GE_CUDA(cudaSetDevice(ctx->device));
+  lap("release");
 }
 
 }  // namespace ge
