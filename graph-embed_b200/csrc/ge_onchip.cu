@@ -513,6 +513,282 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
   }
 }
 
+// Second-generation cluster solve for the coarsest level (what bounds embed() wall time: 100 000
+// dependent iterations, /root/reference/include/forceatlas.hpp:146-270 called from
+// src/embed.cpp:586).  Same decomposition as k_onchip_cluster; what changed is the length of the
+// dependent chain inside one iteration:
+//   * the pair loop handles U = 8 (or 4) columns per lane and trip with a branch-free clamp and two
+//     accumulator sets, so one warp keeps 8 independent reciprocal-square-root chains in flight
+//     (one warp per scheduler: the instruction-level parallelism has to come from inside it);
+//   * the part of the per-vertex step that depends only on the vertex's own position (|x|, the
+//     gravity factor) is computed between the arrive and the wait of the cluster barrier, where the
+//     warp would otherwise idle for the ~400 cycles the barrier takes;
+//   * DENSE: coarsest graphs of power-law hierarchies are (nearly) complete (R-MAT-20: 54 vertices,
+//     2916 entries), which made the CSR attraction loop as long as the pair loop; the owned rows of
+//     the weight matrix are kept in shared memory and folded into the pair loop (one extra FMA per
+//     pair: d * (c_i c_j repel / r^3 - attract a_ij)).
+template <typename T>
+__device__ __forceinline__ void clamp_branchless(T& r2, T lo);
+template <>
+__device__ __forceinline__ void clamp_branchless<double>(double& r2, double lo) {
+  r2 = Real<double>::clamp_lo(r2, lo);
+}
+template <>
+__device__ __forceinline__ void clamp_branchless<float>(float& r2, float lo) {
+  r2 = fmaxf(r2, lo);
+}
+
+template <typename T, int D, int L, int U, bool GA, bool DENSE>
+__global__ void __launch_bounds__(256) k_onchip_cluster2(const OnchipArgs<T> a, int per_cta) {
+  namespace cg = cooperative_groups;
+  constexpr int NM = Real<T>::kMassArrays;
+  using C = Col<T, D>;
+  constexpr int DP = C::DP, MP = C::MP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[32];
+  __shared__ double bc[D + 1];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+
+  const int4 task = a.tasks[0];
+  const int s = task.y;
+  const int S = onchip_spad(s, L, U);
+  const int WS = S + 8;                      // row stride of the weight rows (bank spread)
+  T* pos = reinterpret_cast<T*>(smem_raw);   // [2][S][DP]
+  T* ms = pos + 2 * S * DP;                  // [S][MP]
+  T* Wm = ms + S * MP;                       // DENSE: [per_cta][WS]  attract * a_ij of the owned rows
+
+  const int tid = threadIdx.x;
+  const int lv = tid / L, part = tid % L;
+  const int gv = rank * per_cta + lv;
+  const bool owner = lv < per_cta && gv < s;
+  const int slot = owner ? gv : 0;
+  const Physics<T> ph = a.ph;
+
+  T x[D], fprev[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    x[k] = (T)a.init_aos[(int64_t)slot * D + k];
+    fprev[k] = (T)0;
+  }
+  const T ci = a.mass[slot];
+  const T ci_repel = ci * ph.repel;
+  const int eb = owner ? a.e_begin[slot] : 0;
+  const int ee = owner ? a.e_end[slot] : 0;
+  int ej[2] = {0, 0};
+  T ew[2] = {(T)0, (T)0};
+  if (!DENSE) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = eb + part + q * L;
+      if (e < ee) {
+        ej[q] = a.e_idx[e];
+        ew[q] = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+      }
+    }
+  }
+  const int smem_elems = 2 * S * DP + S * MP + (DENSE ? per_cta * WS : 0);
+  for (int i = tid; i < smem_elems; i += blockDim.x) pos[i] = (T)0;
+  __syncthreads();
+  for (int i = tid; i < s; i += blockDim.x) {  // every CTA loads the whole graph's state
+#pragma unroll
+    for (int k = 0; k < D; ++k) pos[i * DP + k] = (T)a.init_aos[(int64_t)i * D + k];
+    const T c = a.mass[i];
+    ms[i * MP] = c;
+    if (NM > 1) ms[i * MP + (NM > 1 ? 1 : 0)] = (T)1.5 * c;
+    if (NM > 2) ms[i * MP + (NM > 2 ? 2 : 0)] = (T)1.875 * c;
+  }
+  if (DENSE && owner) {
+    for (int e = eb + part; e < ee; e += L) {
+      const T w = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+      atomicAdd(&Wm[lv * WS + a.e_idx[e]], ph.attract * w);
+    }
+  }
+  cluster.sync();  // also: nobody writes into a peer's shared memory before it is initialised
+  const T* wrow = Wm + (owner ? lv : 0) * WS;
+
+  const T* pc = pos;
+  T* pn = pos + S * DP;
+  int nxt = 1;
+  // own-position part of the step (:205-211): 1/|x| and the gravity factor
+  T m2 = (T)0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
+  T grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
+  for (int it = 0; it < a.iters; ++it) {
+    T f0[D], f1[D], fa[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f0[k] = f1[k] = fa[k] = (T)0;
+    if (!DENSE && owner) {  // attraction entries held in registers: independent of the pair loop
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (eb + part + q * L < ee) {
+          T xj[D], d[D];
+          C::pos(pc, ej[q], xj);
+          T r2 = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[k] = xj[k] - x[k];
+            r2 = fma(d[k], d[k], r2);
+          }
+          const T g = attraction_factor<T, GA>(r2, ew[q], ci, ph);
+#pragma unroll
+          for (int k = 0; k < D; ++k) fa[k] = fma(d[k], g, fa[k]);
+        }
+      }
+    }
+    // every lane runs the pair loop (lanes without a vertex compute a discarded row)
+    for (int j0 = part; j0 < S; j0 += L * U) {
+      T d[U][D], r2[U], s3[U], m0[U], m1[U], m2c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * L;
+        T xj[D];
+        C::pos(pc, j, xj);
+        C::mass(ms, j, m0[u], m1[u], m2c[u]);
+        r2[u] = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          d[u][k] = x[k] - xj[k];
+          r2[u] = fma(d[u][k], d[u][k], r2[u]);
+        }
+        clamp_branchless<T>(r2[u], ph.eps2);
+      }
+      Real<T>::template inv_cube_mass_v<U>(r2, m0, m1, m2c, s3);
+      if (DENSE) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) s3[u] = fma(s3[u], ci_repel, -wrow[j0 + u * L]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u += 2) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          f0[k] = fma(d[u][k], s3[u], f0[k]);
+          f1[k] = fma(d[u + 1][k], s3[u + 1], f1[k]);
+        }
+      }
+    }
+    T f[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = DENSE ? f0[k] + f1[k] : fma(f0[k] + f1[k], ci_repel, fa[k]);
+    if (!DENSE && owner) {
+      // (entries beyond two per lane continue from the compact list through L1)
+      for (int e = eb + part + 2 * L; e < ee; e += L) {
+        const int j = a.e_idx[e];
+        const T w = (a.e_w != nullptr && ph.use_weights) ? a.e_w[e] : (T)1;
+        T xj[D], d[D];
+        C::pos(pc, j, xj);
+        T r2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          d[k] = xj[k] - x[k];
+          r2 = fma(d[k], d[k], r2);
+        }
+        const T g = attraction_factor<T, GA>(r2, w, ci, ph);
+#pragma unroll
+        for (int k = 0; k < D; ++k) f[k] = fma(d[k], g, f[k]);
+      }
+    }
+#pragma unroll
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
+    }
+    {  // :205-261 with the gravity factor prepared ahead (flat kernel: |x| and swing unclamped)
+      T sw2 = (T)0, f2 = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const T fk = fma(-x[k], grav, f[k]);
+        const T dk = fk - fprev[k];
+        sw2 = fma(dk, dk, sw2);
+        f2 = fma(fk, fk, f2);
+        f[k] = fk;
+      }
+      const T swing = sw2 > (T)0 ? sw2 * Real<T>::rsqrt_acc(sw2) : sw2;
+      const T ssw = swing > (T)0 ? swing * Real<T>::rsqrt_acc(swing) : swing;
+      T speed = ph.ks * ph.gspeed * Real<T>::rcp_acc((T)1 + ph.gspeed * ssw);
+      const T cap = ph.ksmax * Real<T>::rsqrt_acc(f2);
+      if (speed > cap) speed = cap;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        x[k] = fma(f[k], speed, x[k]);
+        fprev[k] = f[k];
+      }
+    }
+    if (owner) {  // the L lanes of the group share out the csize peer stores
+      for (int rr = part; rr < csize; rr += L) {
+        T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[k] = x[k];
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // between arrive and wait: what the next iteration needs from the vertex's own new position
+    m2 = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
+    grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const T* tmp = pc;
+    pc = pn;
+    pn = const_cast<T*>(tmp);
+    nxt ^= 1;
+  }
+
+  if (!a.normalize) {
+    if (owner && part == 0) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.out_aos[(int64_t)gv * D + k] = (double)x[k];
+    }
+    return;
+  }
+  if (rank != 0) return;  // include/forceatlas.hpp:272-303 by CTA 0 (every CTA holds all positions)
+  auto block_reduce = [&](double val, bool is_max) -> double {
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, val, off);
+      val = is_max ? fmax(val, o) : val + o;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid < 32) {
+      double w = (tid < (int)((blockDim.x + 31) >> 5)) ? red[tid] : 0.0;
+      for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, w, off);
+        w = is_max ? fmax(w, o) : w + o;
+      }
+      if (tid == 0) red[0] = w;
+    }
+    __syncthreads();
+    const double out = red[0];
+    __syncthreads();
+    return out;
+  };
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    double part_sum = 0.0;
+    for (int i = tid; i < s; i += blockDim.x) part_sum += (double)pc[i * DP + k];
+    const double tot = block_reduce(part_sum, false);
+    if (tid == 0) bc[k] = tot / s;
+  }
+  __syncthreads();
+  double mx = 0.0;
+  for (int i = tid; i < s; i += blockDim.x) {
+    double mm = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = (double)pc[i * DP + k] - bc[k];
+      mm += c * c;
+    }
+    mx = fmax(mx, sqrt(mm));
+  }
+  const double maxlen = block_reduce(mx, true);
+  for (int i = tid; i < s; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      a.out_aos[(int64_t)i * D + k] = ((double)pc[i * DP + k] - bc[k]) / maxlen;
+  }
+}
+
 constexpr int kWarpsPerCta = 8;
 
 template <typename T, int D>
@@ -709,10 +985,67 @@ const void* cluster_kernel(int L) {
 }
 }  // namespace
 
+namespace {
+template <typename T, int D, int L>
+const void* cluster2_kernel_l(int U, bool ga, bool dense) {
+  if (ga) return (const void*)k_onchip_cluster2<T, D, L, 4, true, false>;
+  if (dense) return U == 8 ? (const void*)k_onchip_cluster2<T, D, L, 8, false, true>
+                           : (const void*)k_onchip_cluster2<T, D, L, 4, false, true>;
+  return U == 8 ? (const void*)k_onchip_cluster2<T, D, L, 8, false, false>
+                : (const void*)k_onchip_cluster2<T, D, L, 4, false, false>;
+}
+template <typename T, int D>
+const void* cluster2_kernel(int L, int U, bool ga, bool dense) {
+  return L == 16 ? cluster2_kernel_l<T, D, 16>(U, ga, dense) : cluster2_kernel_l<T, D, 8>(U, ga, dense);
+}
+int env_or(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+}  // namespace
+
 // The whole flat problem on one cluster of `csize` CTAs (slot == vertex id).
 template <typename T>
-void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int dim, int csize) {
+void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int dim, int csize, int64_t nnz) {
   const int per_cta = (n + csize - 1) / csize;
+  const bool ga = a.ph.general_attraction != 0;
+  // ---- second-generation kernel: 8 or 16 lanes per vertex, at most 256 threads per CTA ----------
+  if (env_or("GE_K3_V1", 0) == 0 && per_cta * 8 <= 256) {
+    int L = per_cta * 16 <= 128 ? 16 : 8;
+    if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::atoi(v) >= 16 ? 16 : 8;
+    if (per_cta * L > 256) L = 8;
+    // columns per lane and trip: 8 when a lane owns at least 8 columns
+    int U = ((n + L - 1) / L) >= 8 ? 8 : 4;
+    U = env_or("GE_K3_U", U) >= 8 ? 8 : 4;
+    // (nearly) complete coarse graphs: more than two attraction entries per lane on average
+    bool dense = !ga && nnz > (int64_t)2 * L * n && n <= 256;
+    if (const char* v = std::getenv("GE_K3_DENSE")) dense = !ga && std::atoi(v) != 0;
+    if (ga) U = 4;
+    const int threads = (int)round_up((int64_t)per_cta * L, 32);
+    const void* fn = dim == 2 ? cluster2_kernel<T, 2>(L, U, ga, dense) : cluster2_kernel<T, 3>(L, U, ga, dense);
+    const int S = onchip_spad(n, L, U);
+    const int DP = dim == 2 ? 2 : 4, MP = sizeof(T) == 8 ? 4 : 1;
+    const size_t smem = ((size_t)(2 * DP + MP) * S + (dense ? (size_t)per_cta * (S + 8) : 0)) * sizeof(T);
+    if (smem > 40 * 1024)
+      GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* args[] = {(void*)&a, (void*)&per_cta};
+    GE_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    ctx->launches++;
+    return;
+  }
   // measured (tools/profile_small.py k3sweep): 8 lanes per vertex, as in the single-CTA kernel
   // (n = 73: 8 CTAs x 8 lanes 1.3 us/iteration vs 2.2 us on one CTA; n = 157: 1.8 us)
   // (16 lanes: one trip of the pair loop instead of two up to n = 64 -- 1.11 vs 1.17 us at n = 64,
@@ -727,12 +1060,12 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   while (L > 1 && per_cta * L > 512) L /= 2;
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
   GE_REQUIRE(threads <= 512, "cluster solve: too many vertices per CTA");
-  const bool ga = a.ph.general_attraction != 0;
   const void* fn = dim == 2 ? (ga ? cluster_kernel<T, 2, true>(L) : cluster_kernel<T, 2, false>(L))
                             : (ga ? cluster_kernel<T, 3, true>(L) : cluster_kernel<T, 3, false>(L));
   const size_t smem = cta_smem<T>(dim, n, L, false);
-  if (smem > 40 * 1024)  // (static shared memory counts against the 48 KB default limit too)
+  if (smem > 40 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (csize > 8) GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(csize);
   cfg.blockDim = dim3(threads);
@@ -829,10 +1162,10 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   if (!forces_only) {
     csize = n >= 64 ? 8 : n >= 40 ? 4 : 1;
     if (const char* v = std::getenv("GE_CLUSTER")) csize = std::atoi(v);
-    csize = std::max(1, std::min(csize, 8));
+    csize = std::max(1, std::min(csize, 16));
   }
   if (csize > 1)
-    launch_onchip_cluster<T>(ctx, a, n, dim, csize);
+    launch_onchip_cluster<T>(ctx, a, n, dim, csize, nnz);
   else
     launch_onchip_cta<T>(ctx, a, 1, dim, false, L, threads, n);
   if (keep == nullptr) d_out.download(ctx, forces_only ? forces_out : coords, (size_t)n * dim);

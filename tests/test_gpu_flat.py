@@ -175,6 +175,7 @@ def test_cluster_solve_matches_single_cta(ctx, capi, oracle, csize, dim, monkeyp
     reference positions."""
     A, z = load_flat_golden()
     monkeypatch.setenv("GE_ONCHIP_MAX", "1024")
+    monkeypatch.setenv("GE_K3_V1", "1")         # the first-generation cluster kernel
     monkeypatch.setenv("GE_ONCHIP_LANES", "4")  # same lane count -> same summation order
     x0 = z["x0_d%d" % dim]
     for k in (1, 25):
@@ -183,6 +184,52 @@ def test_cluster_solve_matches_single_cta(ctx, capi, oracle, csize, dim, monkeyp
         monkeypatch.setenv("GE_CLUSTER", str(csize))
         xc = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k))
         assert np.array_equal(x1, xc), np.abs(x1 - xc).max()
+
+
+@pytest.mark.parametrize("csize,lanes,u", [(4, 8, 4), (8, 8, 8), (8, 16, 4), (16, 16, 8), (8, 8, 4)])
+@pytest.mark.parametrize("dense", [0, 1])
+def test_cluster_solve_v2_against_golden(ctx, capi, oracle, csize, lanes, u, dense, monkeypatch):
+    """The second-generation cluster kernel (8 columns per lane and trip, own-position work inside
+    the barrier, optional dense weight rows folded into the pair loop) in every launch shape:
+    the compiled reference's golden positions within the chaos-aware bound, d = 2 and 3."""
+    A, z = load_flat_golden()
+    monkeypatch.setenv("GE_ONCHIP_MAX", "1024")
+    monkeypatch.setenv("GE_CLUSTER", str(csize))
+    monkeypatch.setenv("GE_ONCHIP_LANES", str(lanes))
+    monkeypatch.setenv("GE_K3_U", str(u))
+    monkeypatch.setenv("GE_K3_DENSE", str(dense))
+    for dim in (2, 3):
+        x0 = z["x0_d%d" % dim]
+        for k in (1, 5, 25):
+            ref = z["x_d%d_k%d" % (dim, k)]
+            sign = np.random.default_rng(0).choice([-1.0, 1.0], size=x0.shape)
+            pert, _ = oracle.flat_run(A, dim, x0 * (1 + sign * 2.2e-16), oracle.Params(iterations=k))
+            tol = max(1e-12, 50 * np.abs(pert - ref).max())
+            x = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k))
+            assert np.abs(x - ref).max() < tol, (dim, k, np.abs(x - ref).max(), tol)
+
+
+def test_dense_weighted_coarse_graph_with_self_loops(ctx, capi, oracle, graphs):
+    """A coarsest level as power-law hierarchies produce it: (nearly) complete, real weights,
+    diagonal entries (quirk Q5).  The default launch picks the dense variant; positions after k
+    iterations against the oracle within the chaos-aware bound, plus normalize and options."""
+    rng = np.random.default_rng(3)
+    n = 54
+    M = rng.random((n, n)) * (rng.random((n, n)) < 0.9)
+    M = M + M.T + np.diag(rng.random(n) * 5)
+    import scipy.sparse as sp
+    A = graphs.canonical(sp.csr_matrix(M))
+    for dim in (2, 3):
+        x0 = capi.reference_uniform(9, n * dim).reshape(n, dim)
+        for k in (1, 3, 10):
+            for kw in (dict(), dict(normalize=1), dict(attract=0.5, repel=2.0, gravity=0.3)):
+                okw = dict(kw)
+                ref, _ = oracle.flat_run(A, dim, x0, oracle.Params(iterations=k, **okw))
+                sign = np.random.default_rng(0).choice([-1.0, 1.0], size=x0.shape)
+                pert, _ = oracle.flat_run(A, dim, x0 * (1 + sign * 2.2e-16), oracle.Params(iterations=k, **okw))
+                tol = max(1e-12, 50 * np.abs(pert - ref).max())
+                x = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=k, **kw))
+                assert np.abs(x - ref).max() < tol, (dim, k, kw, np.abs(x - ref).max(), tol)
 
 
 def test_internal_renumbering_is_transparent(ctx, capi, oracle, graphs, monkeypatch):

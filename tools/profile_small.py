@@ -52,6 +52,50 @@ elif mode == "k3sweep":
                 ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters, precision=prec))
                 ts.append(time.time() - t)
             print("n=%d nnz=%d cluster=%d L=%d: %.3f us/iter (overhead %.2f ms)" % (n, Ac.nnz, cs, L, 1e6 * (ts[1] - ts[0]) / 20000, 1e3 * ts[0]), flush=True)
+elif mode == "k3v2":
+    # us/iteration of the coarsest-level solve: first- vs second-generation cluster kernel over
+    # cluster size x lanes x columns per trip, at n ~ 34, 64, 100, 157 and on the dense 54-vertex
+    # coarsest graph of a power-law hierarchy
+    import time
+    import scipy.sparse as sp
+    dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    cases = []
+    for target in (34, 64, 100, 157):
+        A = graphs.rgg(40 * target, 10.0, seed=1)
+        As, Ps = graphs.coarsen(A, 0.25, min_coarse=target)
+        cases.append(("rgg-coarse", As[-1]))
+    rng = np.random.default_rng(3)
+    M = rng.random((54, 54))
+    cases.append(("dense54", graphs.canonical(sp.csr_matrix(M + M.T))))
+
+    def measure(Ac, env):
+        for k in ("GE_K3_V1", "GE_CLUSTER", "GE_ONCHIP_LANES", "GE_K3_U", "GE_K3_DENSE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        n = Ac.shape[0]
+        x0 = capi.reference_uniform(1, n * dim).reshape(-1, dim)
+        ts = []
+        for iters in (1, 20001):
+            ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters))
+            t = time.time()
+            ctx.flat_forceatlas(Ac, dim, x0, capi.flat_params(iterations=iters))
+            ts.append(time.time() - t)
+        return 1e6 * (ts[1] - ts[0]) / 20000
+
+    for name, Ac in cases:
+        n = Ac.shape[0]
+        print("%s n=%d nnz=%d d=%d" % (name, n, Ac.nnz, dim), flush=True)
+        print("   default (auto)            : %.3f us/iter" % measure(Ac, {}), flush=True)
+        print("   v1 default                : %.3f us/iter" % measure(Ac, {"GE_K3_V1": "1"}), flush=True)
+        for cs in (4, 8, 16):
+            for L in (8, 16):
+                if (n + cs - 1) // cs * L > 256:
+                    continue
+                for U in (4, 8):
+                    for dense in ((0, 1) if Ac.nnz > 8 * n else (0,)):
+                        t = measure(Ac, {"GE_CLUSTER": str(cs), "GE_ONCHIP_LANES": str(L), "GE_K3_U": str(U),
+                                         "GE_K3_DENSE": str(dense)})
+                        print("   v2 cluster=%2d L=%2d U=%d dense=%d: %.3f us/iter" % (cs, L, U, dense, t), flush=True)
 elif mode == "k3parts":
     import time
     for target, dim in ((42, 3), (34, 2), (91, 2)):
