@@ -1009,17 +1009,22 @@ template <typename T>
 void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int dim, int csize, int64_t nnz) {
   const int per_cta = (n + csize - 1) / csize;
   const bool ga = a.ph.general_attraction != 0;
-  // ---- second-generation kernel: 8 or 16 lanes per vertex, at most 256 threads per CTA ----------
-  if (env_or("GE_K3_V1", 0) == 0 && per_cta * 8 <= 256) {
-    int L = per_cta * 16 <= 128 ? 16 : 8;
+  // ---- second-generation kernel (dense coarse graphs): 8 or 16 lanes per vertex, <= 256 threads ----
+  // Measured (tools/profile_small.py k3v2, profiles/r02_k3v2_d2.txt): on the (nearly) complete
+  // 54-vertex coarsest graph of a power-law hierarchy the dense variant takes 1.00 us/iteration
+  // (8 CTAs x 16 lanes, 4 columns per trip) against 1.72 for the first-generation kernel, whose CSR
+  // attraction loop is as long as its pair loop there.  On sparse coarse graphs (~6 entries per
+  // row) the first-generation kernel stays ahead in every shape (n = 100: 1.51 vs 1.57-2.0 us), so
+  // it keeps serving them: GE_K3_V2=1 forces the new kernel, GE_K3_V1=1 the old one.
+  bool dense = !ga && nnz > (int64_t)2 * 8 * n && n <= 256;
+  if (const char* v = std::getenv("GE_K3_DENSE")) dense = !ga && std::atoi(v) != 0;
+  const bool want_v2 = env_or("GE_K3_V1", 0) == 0 && (dense || env_or("GE_K3_V2", 0) != 0 ||
+                                                       std::getenv("GE_K3_DENSE") != nullptr);
+  if (want_v2 && per_cta * 8 <= 256) {
+    int L = per_cta * 16 <= 256 ? 16 : 8;
     if (const char* v = std::getenv("GE_ONCHIP_LANES")) L = std::atoi(v) >= 16 ? 16 : 8;
     if (per_cta * L > 256) L = 8;
-    // columns per lane and trip: 8 when a lane owns at least 8 columns
-    int U = ((n + L - 1) / L) >= 8 ? 8 : 4;
-    U = env_or("GE_K3_U", U) >= 8 ? 8 : 4;
-    // (nearly) complete coarse graphs: more than two attraction entries per lane on average
-    bool dense = !ga && nnz > (int64_t)2 * L * n && n <= 256;
-    if (const char* v = std::getenv("GE_K3_DENSE")) dense = !ga && std::atoi(v) != 0;
+    int U = env_or("GE_K3_U", 4) >= 8 ? 8 : 4;
     if (ga) U = 4;
     const int threads = (int)round_up((int64_t)per_cta * L, 32);
     const void* fn = dim == 2 ? cluster2_kernel<T, 2>(L, U, ga, dense) : cluster2_kernel<T, 3>(L, U, ga, dense);
@@ -1161,6 +1166,8 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   int csize = 1;
   if (!forces_only) {
     csize = n >= 64 ? 8 : n >= 40 ? 4 : 1;
+    if ((int64_t)nnz > (int64_t)16 * n && !a.ph.general_attraction && n <= 256)  // dense: see launch_onchip_cluster
+      csize = n >= 40 ? 8 : n >= 24 ? 4 : 1;
     if (const char* v = std::getenv("GE_CLUSTER")) csize = std::atoi(v);
     csize = std::max(1, std::min(csize, 16));
   }
