@@ -350,6 +350,8 @@ def run_ours(args):
             out["roofline_attraction_large"] = bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src)
         if not args.no_embed:
             out["embed"] = bench_embed(args, capi, ctx, graphs)
+        if not args.no_embed and not args.no_refhier:
+            out["embed_config3"] = bench_embed_refhier(args, capi, ctx, graphs)
         if not args.no_galerkin:
             out["galerkin"] = bench_galerkin(args, capi, ctx, graphs, hbm_peak, hbm_src)
         if not args.no_cpu:
@@ -622,6 +624,45 @@ def bench_embed(args, capi, ctx, graphs):
     return out
 
 
+def bench_embed_refhier(args, capi, ctx, graphs):
+    """BASELINE config 3 on the hierarchy of the REFERENCE's own partitioner (R-MAT scale 20,
+    largest component, coarsening 0.25, d = 3; tests/golden/refhier_rmat20.npz): embed() wall time
+    with the device-side phases.  The compiled reference's embed() on the same hierarchy takes
+    minutes (profiles/r02_config3_rmat20_ref.json: 213.7 s on 16 host threads) and is not re-run
+    here."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import load_ref_hierarchy
+    t = time.time()
+    As, Ps, meta = load_ref_hierarchy(graphs, "rmat20")
+    log("[bench] config3 reference hierarchy %s (%.1fs)" % ([a.shape[0] for a in As], time.time() - t))
+    ctx.embed(As, Ps, 3, seed=0, coarse_iterations=1000)  # warm-up
+    walls, st = [], None
+    for rep in range(3):
+        t = time.time()
+        x, st = ctx.embed(As, Ps, 3, seed=0)
+        walls.append(time.time() - t)
+    assert np.isfinite(x).all()
+    sizes = [int(np.diff(P.indptr).max()) for P in Ps]
+    pairs = [float((np.diff(P.indptr).astype(np.int64) * (np.diff(P.indptr) - 1)).sum()) for P in Ps]
+    ref_s, ref_threads = None, None
+    prof = os.path.join(ROOT, "profiles", "r02_config3_rmat20_ref.json")
+    if os.path.exists(prof):
+        d = json.load(open(prof))
+        if d.get("cpu_reference"):
+            ref_s, ref_threads = d["cpu_reference"]["embed_wall_s"], d["cpu_reference"]["threads"]
+    return {"workload": "config3: R-MAT scale 20 largest component (n=%d, %d entries), hierarchy of the "
+                        "reference partitioner, multilevel embed, dim=3" % (As[0].shape[0], As[0].nnz),
+            "levels": [a.shape[0] for a in As], "max_aggregate": sizes, "pairs_per_iteration": pairs,
+            "embed_wall_s": float(np.median(walls)), "coarse_ms": st["coarse_ms"], "levels_ms": st["levels_ms"],
+            "grid_tier_ms": st["grid_tier_ms"], "device_radii_ms": st["device_radii_ms"],
+            "host_radii_ms": st["host_radii_ms"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"],
+            "pair_interactions": st["pair_interactions"],
+            "pair_interactions_per_sec": st["pair_interactions"] / float(np.median(walls)),
+            "kernel_launches": st["kernel_launches"],
+            "cpu_reference_embed_wall_s_recorded": ref_s, "cpu_reference_threads_recorded": ref_threads,
+            "cpu_reference_source": "profiles/r02_config3_rmat20_ref.json (tools/run_config.py config3 --ref --cpu-ref)"}
+
+
 def bench_cpu_baseline(args):
     """The reference's own flat forceAtlas (oracle/_ref, -O3, OpenMP, all host threads) on a bounded
     sample of the same workload, ~10-30 s of CPU work."""
@@ -661,6 +702,7 @@ def main():
     ap.add_argument("--ordered", action="store_true",
                     help="N > 1: ordered row-block sweep instead of the symmetric pair shares")
     ap.add_argument("--no-embed", action="store_true")
+    ap.add_argument("--no-refhier", action="store_true", help="skip config 3 on the reference hierarchy")
     ap.add_argument("--no-galerkin", action="store_true")
     ap.add_argument("--galerkin-n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")

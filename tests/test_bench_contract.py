@@ -32,7 +32,8 @@ def test_reference_arm_contract():
 
 @pytest.mark.gpu
 def test_gpu_arm_contract():
-    d = _one_json_line(["--steps", "3", "--warmup", "3", "--n", "40000", "--attr-n", "150000", "--galerkin-n", "60000"], 600)
+    d = _one_json_line(["--steps", "3", "--warmup", "3", "--n", "40000", "--attr-n", "150000", "--galerkin-n", "60000",
+                        "--no-refhier"], 600)
     assert BASE_KEYS <= set(d)
     assert {"roofline", "clocks", "gpu_launches", "embed", "fp32"} <= set(d)
     assert d["dtype"] == "f64" and d["scaling"] == "strong" and d["n_gpus"] == 1
@@ -43,3 +44,4 @@ def test_gpu_arm_contract():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["parity_ok"] and d["parity_max_err"] < 1e-10 and d["parity_rows_checked"] >= 32
