@@ -542,10 +542,39 @@ def bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src):
         if w == 8 and dim == 3 and n > 1_900_000 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("k_attract_step_f64_d3_n2m_bytes_per_launch")
         out[name] = {"kernel": "k_attract_step_staged<%s,%d>" % ("double" if w == 8 else "float", dim), "bound": "hbm",
+                     "graph": "RGG n=%d avg degree 10 (the graph the launch shape was tuned on)" % n,
                      "traffic": traffic,
                      "unit": "GB/s", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                      "frac": b / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms,
                      "bytes_per_launch": b, "n": n, "nnz": nnz, "edge_visits_per_sec": nnz / (ms * 1e-3)}
+    # held-out graphs: not used for any tuning decision (another generator, another degree
+    # distribution); same frozen launch heuristics
+    held = []
+    t = time.time()
+    held.append(("heldout_delaunay3d", "Delaunay tetrahedralisation, %d points (avg degree ~15.5)" % args.heldout_n,
+                 graphs.delaunay3d(args.heldout_n, seed=3)))
+    held.append(("heldout_rmat", "R-MAT scale %d, edge factor 16, largest component (power-law rows)" % args.heldout_rmat,
+                 graphs.rmat(args.heldout_rmat, 16, seed=5)))
+    log("[bench] held-out attraction graphs (%.1fs)" % (time.time() - t))
+    for key, desc, H in held:
+        hn, hnnz = H.shape[0], H.nnz
+        for dim in (2, 3):
+            plan = ctx.flat_plan(H, dim, capi.flat_params(precision=capi.GE_F64))
+            plan.upload(capi.reference_uniform(5, hn * dim).reshape(hn, dim))
+            plan.select_kernels(2)
+            plan.iterate(2)
+            plan.sync()
+            plan.profile(True)
+            plan.iterate(5)
+            prof = plan.profile_get()
+            plan.close()
+            ms = prof["attract_step_ms"] / prof["attract_step_launches"]
+            b = algorithmic(hn, hnnz, dim, 8)["step_bytes"]
+            out["%s_f64_d%d" % (key, dim)] = {
+                "kernel": "k_attract_step*<double,%d>" % dim, "bound": "hbm", "graph": desc, "traffic": None,
+                "unit": "GB/s", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "frac": b / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms,
+                "bytes_per_launch": b, "n": hn, "nnz": hnnz, "edge_visits_per_sec": hnnz / (ms * 1e-3)}
     return out
 
 
@@ -699,6 +728,8 @@ def main():
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--ref-n", type=int, default=30_000)
     ap.add_argument("--attr-n", type=int, default=2_000_000)
+    ap.add_argument("--heldout-n", type=int, default=1_000_000, help="points of the held-out Delaunay graph")
+    ap.add_argument("--heldout-rmat", type=int, default=20, help="scale of the held-out R-MAT graph")
     ap.add_argument("--ordered", action="store_true",
                     help="N > 1: ordered row-block sweep instead of the symmetric pair shares")
     ap.add_argument("--no-embed", action="store_true")

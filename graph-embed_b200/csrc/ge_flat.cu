@@ -13,6 +13,7 @@
 // tile) so every access is coalesced and each array of a column tile is one contiguous bulk copy.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -261,9 +262,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
   // Issue every load whose address is known up front before walking the row, so the row's
   // index -> coordinate gather chain overlaps them (the kernel is latency-, not issue-bound).
   const int e0 = active ? a.e_begin[r] : 0;
-  const int e1 = active ? a.e_end[r] : 0;
+  int e1 = active ? a.e_end[r] : 0;
+  const bool is_long = a.long_threshold > 0 && e1 - e0 > a.long_threshold;  // k_attract_step_long's
+  if (is_long) e1 = e0;
   T x[D], f[D], frep[D], fprev[D], E[D];
-  const bool finisher = active && lane == 0;
+  const bool finisher = active && lane == 0 && !is_long;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     x[k] = a.pos_cur[(int64_t)k * a.ld + i];
@@ -414,7 +417,9 @@ __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArg
     const int r = c * RPC + rl;
     const bool active = r < a.nrows;
     const int i = a.row0 + (active ? r : 0);
-    const bool finisher = active && lane == 0;
+    const bool is_long = a.long_threshold > 0 && e1 - e0 > a.long_threshold;  // k_attract_step_long's
+    if (is_long) e1 = e0;
+    const bool finisher = active && lane == 0 && !is_long;
     T x[D], f[D], frep[D], fprev[D];
     const int64_t ldr = a.ldr ? a.ldr : a.ldf;
 #pragma unroll
@@ -527,6 +532,98 @@ __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArg
     __syncthreads();  // everyone has left this chunk's stage: the copy issued next trip may refill it
     c = cn;
     b0 = nb0, b1 = nb1, nb0 = nnb0, nb1 = nnb1, e0 = ne0, e1 = ne1;
+  }
+}
+
+// K1b+c for the long rows of power-law graphs: one CTA per row.  All threads walk the row's entries
+// (coalesced index / weight loads, 4 gathers in flight per thread), the partial sums are combined in
+// a fixed order (lane tree, then warps in order: bit-reproducible) and thread 0 finishes the row
+// exactly like the row kernels do.
+constexpr int kLongThreads = 512;
+template <typename T, int D, bool GA>
+__global__ void __launch_bounds__(kLongThreads) k_attract_step_long(const StepArgs<T> a,
+                                                                    const int* __restrict__ rows) {
+  __shared__ T red[D][kLongThreads / 32];
+  const int r = rows[blockIdx.x];
+  const int i = a.row0 + r;
+  const int tid = threadIdx.x;
+  const int e0 = a.e_begin[r], e1 = a.e_end[r];
+  const bool weighted = a.W != nullptr && a.ph.use_weights;
+  T x[D], f[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    x[k] = a.pos_cur[(int64_t)k * a.ld + i];
+    f[k] = (T)0;
+  }
+  const T ci = a.mass[i];
+  constexpr int EU = 4;
+  for (int e = e0 + tid; e < e1; e += EU * kLongThreads) {
+    int jn[EU];
+    T wn[EU];
+    bool on[EU];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      const int eu = e + u * kLongThreads;
+      on[u] = eu < e1;
+      jn[u] = on[u] ? a.J[eu] : i;
+      wn[u] = (on[u] && weighted) ? a.W[eu] : (T)1;
+    }
+    T dn[EU][D];
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      if (a.aos_cur != nullptr) {
+        Gather<T, D>::ld(a.aos_cur, jn[u], dn[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) dn[u][k] = a.pos_cur[(int64_t)k * a.ld + jn[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EU; ++u) {
+      T r2 = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        dn[u][k] -= x[k];
+        r2 = fma(dn[u][k], dn[u][k], r2);
+      }
+      const T g = on[u] ? attraction_factor<T, GA>(r2, wn[u], ci, a.ph) : (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) f[k] = fma(dn[u][k], g, f[k]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) red[k][tid >> 5] = f[k];
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  T frep[D], fprev[D];
+  const int64_t ldr = a.ldr ? a.ldr : a.ldf;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    T acc = (T)0;
+    for (int w = 0; w < kLongThreads / 32; ++w) acc += red[k][w];
+    frep[k] = a.Frep[(int64_t)k * ldr + r];
+    if (a.frep_scale != (T)0) frep[k] *= ci * a.frep_scale;
+    fprev[k] = a.update ? a.Fprev[(int64_t)k * a.ldf + r] : (T)0;
+    f[k] = acc + frep[k];
+  }
+  const T E[D] = {};
+  vertex_step<T, D, false>(x, f, fprev, E, ci, a.ph);
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    a.Fprev[(int64_t)k * a.ldf + r] = fprev[k];
+    if (a.update) a.pos_next[(int64_t)k * a.ld + i] = x[k];
+  }
+  if (a.update && a.aos_next != nullptr) {
+    constexpr int DP = Gather<T, D>::DP;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) a.aos_next[(int64_t)i * DP + k] = k < D ? x[k] : (T)0;
   }
 }
 
@@ -819,6 +916,23 @@ void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int gro
   ctx->launches++;
 }
 
+template <typename T>
+void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong) {
+  if (nlong == 0) return;
+  const bool ga = a.ph.general_attraction != 0;
+  if (dim == 2) {
+    if (ga) k_attract_step_long<T, 2, true><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+    else k_attract_step_long<T, 2, false><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+  } else {
+    if (ga) k_attract_step_long<T, 3, true><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+    else k_attract_step_long<T, 3, false><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+  }
+  GE_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+template void launch_attract_step_long<double>(ge_context*, const StepArgs<double>&, int, const int*, int);
+template void launch_attract_step_long<float>(ge_context*, const StepArgs<float>&, int, const int*, int);
+
 template void launch_attract_step<double>(ge_context*, const StepArgs<double>&, int, int, bool);
 template void launch_attract_step<float>(ge_context*, const StepArgs<float>&, int, int, bool);
 
@@ -938,8 +1052,44 @@ class FlatSolverT final : public FlatSolver {
         W_.upload(ctx, w.data(), lnnz);
       }
     }
+    // Rows far longer than the rest (power-law graphs) get a CTA each; the row kernels skip them.
+    {
+      long_threshold_ = env_int("GE_LONG_ROW", 512);
+      std::vector<int> lrows;
+      int64_t long_entries = 0;
+      if (long_threshold_ > 0)
+        for (int r = 0; r < nrows_; ++r)
+          if (rowptr[r + 1] - rowptr[r] > long_threshold_) {
+            lrows.push_back(r);
+            long_entries += rowptr[r + 1] - rowptr[r];
+          }
+      nlong_ = (int)lrows.size();
+      if (nlong_ > 0) {
+        long_rows_.alloc(ctx, lrows.size());
+        long_rows_.upload(ctx, lrows.data(), lrows.size());
+      } else {
+        long_threshold_ = 0;
+      }
+      const int nshort = nrows_ - nlong_;
+      avg_deg_ = nshort > 0 ? double(lnnz - long_entries) / nshort : 0.0;
+      // Gather locality after the renumbering: the mean distance |i - j| over the entries.  2-D
+      // geometric graphs stay within a few hundred positions (the neighbours' coordinates are L1
+      // hits and the SoA gathers are cheapest); 3-D meshes and power-law graphs do not (Delaunay:
+      // ~9000, R-MAT: ~26000), every gathered coordinate then costs a 32-byte L2 sector per
+      // dimension, and the interleaved copy (one sector per neighbour) pays for its extra write.
+      double span = 0.0;
+      for (int r = 0; r < nrows_; ++r)
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) span += std::abs((rb_ + r) - J[e0 + e]);
+      mean_span_ = lnnz > 0 ? span / lnnz : 0.0;
+      if (std::getenv("GE_GATHER_COPY_REORDERED") == nullptr)
+        gather_copy_reordered_ = mean_span_ > env_int("GE_GATHER_SPAN", 2048);
+      if (std::getenv("GE_VERBOSE"))
+        std::fprintf(stderr, "[ge] flat plan rows=%d entries=%d long rows=%d (%.1f%% of the entries) "
+                             "avg degree of the rest %.1f mean |i-j| %.0f gather copy %d\n",
+                     nrows_, lnnz, nlong_, lnnz ? 100.0 * long_entries / lnnz : 0.0, avg_deg_, mean_span_,
+                     (int)(use_gather_copy_ && (perm_.size() == 0 || gather_copy_reordered_)));
+    }
     GE_CUDA(cudaStreamSynchronize(ctx->stream));  // the renumbered host arrays die with this scope
-    avg_deg_ = nrows_ > 0 ? double(lnnz) / nrows_ : 0.0;
 
     aos_[0].alloc(ctx, (size_t)gather_dp() * ld_);
     aos_[1].alloc(ctx, (size_t)gather_dp() * ld_);
@@ -1102,6 +1252,8 @@ class FlatSolverT final : public FlatSolver {
     sa.nrows = nrows_;
     sa.update = update ? 1 : 0;
     sa.ph = ph_;
+    sa.long_threshold = long_threshold_;
+    if ((kernel_mask_ & 2) && nlong_ > 0) launch_attract_step_long<T>(ctx, sa, dim_, long_rows_.get(), nlong_);
     if (kernel_mask_ & 2) {
       // one lane per row while a 256-row chunk fits the staging buffer (fewest instructions per
       // row: measured 58-63 % of the HBM peak against 57-61 % with two lanes), else 2-8 lanes
@@ -1162,7 +1314,9 @@ class FlatSolverT final : public FlatSolver {
   bool staged_step_ = env_int("GE_STEP_STAGED", 1) != 0;
   bool gather_copy_reordered_ = env_int("GE_GATHER_COPY_REORDERED", 0) != 0;
   bool aos_valid_ = false, stepped_ = false;
-  DevBuf<int> rowptr_, J_, perm_;
+  DevBuf<int> rowptr_, J_, perm_, long_rows_;
+  int long_threshold_ = 0, nlong_ = 0;
+  double mean_span_ = 0.0;
   std::unique_ptr<RepulsionPlan<T>> rep_;
   std::unique_ptr<RepulsionSymPlan<T>> sym_;
   DevBuf<T> S_;

@@ -161,12 +161,19 @@ struct StepArgs {
   int64_t ld, ldf;
   int row0, nrows;
   int update;          // 0: only write the total force into Fprev (parity hook)
+  // > 0: rows with more entries than this are left to k_attract_step_long (one CTA per row); the
+  // row kernels skip them entirely.  Power-law graphs: half of the entries of R-MAT-18 sit in the
+  // 2 % of rows longer than 512 entries, the longest has 25 000.
+  int long_threshold = 0;
   Physics<T> ph;
 };
 
 // CSR attraction + gravity + step; `group` lanes per row; ml selects the multilevel clamps.
 template <typename T>
 void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int group, bool ml);
+// The rows listed in `rows` (local row indices, nlong of them), one CTA each (flat physics).
+template <typename T>
+void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong);
 
 int group_for_degree(double avg_deg);
 

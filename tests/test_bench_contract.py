@@ -33,7 +33,7 @@ def test_reference_arm_contract():
 @pytest.mark.gpu
 def test_gpu_arm_contract():
     d = _one_json_line(["--steps", "3", "--warmup", "3", "--n", "40000", "--attr-n", "150000", "--galerkin-n", "60000",
-                        "--no-refhier"], 600)
+                        "--no-refhier", "--heldout-n", "60000", "--heldout-rmat", "14"], 600)
     assert BASE_KEYS <= set(d)
     assert {"roofline", "clocks", "gpu_launches", "embed", "fp32"} <= set(d)
     assert d["dtype"] == "f64" and d["scaling"] == "strong" and d["n_gpus"] == 1

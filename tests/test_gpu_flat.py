@@ -232,6 +232,45 @@ def test_dense_weighted_coarse_graph_with_self_loops(ctx, capi, oracle, graphs):
                 assert np.abs(x - ref).max() < tol, (dim, k, kw, np.abs(x - ref).max(), tol)
 
 
+@pytest.mark.parametrize("long_row", ["512", "48"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_power_law_rows_one_cta_per_long_row(ctx, capi, oracle, graphs, long_row, dim, monkeypatch):
+    """Power-law graphs: rows longer than GE_LONG_ROW entries are handled by one CTA each
+    (k_attract_step_long), the rest by the row kernels; forces and 2-iteration positions against
+    the oracle, weighted and unweighted, with and without the breadth-first renumbering."""
+    monkeypatch.setenv("GE_LONG_ROW", long_row)
+    monkeypatch.setenv("GE_ONCHIP_MAX", "0")
+    A = graphs.rmat(13, 16, seed=4)
+    n = A.shape[0]
+    assert np.diff(A.indptr).max() > 512
+    B = A.copy()
+    B.data = np.random.default_rng(1).uniform(0.2, 3.0, B.nnz)
+    B = graphs.canonical((B + B.T) * 0.5)
+    x0 = capi.reference_uniform(21, n * dim).reshape(n, dim)
+    for M in (A, B):
+        F_ref, S = oracle.flat_forces(M, dim, x0)
+        F = ctx.flat_forces(M, dim, x0, capi.flat_params(), path=1)
+        assert force_error(F, F_ref, S).max() < TOL_F64
+        ref, _ = oracle.flat_run(M, dim, x0, oracle.Params(iterations=2))
+        got = ctx.flat_forceatlas(M, dim, x0, capi.flat_params(iterations=2))
+        assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max()
+    if dim == 3 and long_row == "512":   # a plan large enough to be renumbered (>= 65536 vertices)
+        C = graphs.rmat(17, 16, seed=6)
+        m = C.shape[0]
+        assert m >= 65536
+        y0 = capi.reference_uniform(22, m * dim).reshape(m, dim)
+        plan = ctx.flat_plan(C, dim, capi.flat_params(iterations=100))
+        plan.upload(y0)
+        plan.iterate(1)
+        F = plan.download_forces()
+        plan.close()
+        deg = np.diff(C.indptr)
+        rows = list(np.argsort(deg)[-4:]) + list(np.random.default_rng(0).choice(m, 12, replace=False))
+        for r in rows:
+            F_ref, S = oracle.flat_forces(C, dim, y0, rows=(int(r), int(r) + 1))
+            assert np.linalg.norm(F[r] - F_ref[r]) / S[r] < TOL_F64, (r, int(deg[r]))
+
+
 def test_internal_renumbering_is_transparent(ctx, capi, oracle, graphs, monkeypatch):
     """Single-rank plans on large graphs renumber the vertices breadth-first for gather locality;
     forces and positions come back in the caller's numbering and agree with the un-renumbered
