@@ -350,6 +350,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4 : 6) k_attract_step(co
 // kStepCap entries (very long rows) reads its indices from global memory as before.
 constexpr int kStepCap = 2560;  // staged entries per chunk and stage (multiple of 4: 16-byte copies)
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <typename T, int D, int G, bool GA, int CAP, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArgs<T> a, const int nchunks) {
   constexpr int kStepCap = CAP;
@@ -413,6 +417,23 @@ __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArg
     int nnb0 = 0, nnb1 = 0, ne0 = 0, ne1 = 0;
     if (cnn < nchunks) bounds(cnn, nnb0, nnb1);
     if (has_next) row_range(cn, ne0, ne1);
+    // the next chunk's per-row arrays (own position, pair sums, previous force, mass) are pulled
+    // into L2 now: the first use of x in the walk otherwise waits a full DRAM round trip per chunk
+    // (ncu: the top stall was the DADD that subtracts x from the first gathered neighbour)
+    if (has_next && lane == 0) {
+      const int rn = cn * RPC + rl;
+      if (rn < a.nrows) {
+        const int in = a.row0 + rn;
+        const int64_t ldr_ = a.ldr ? a.ldr : a.ldf;
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) {
+          prefetch_l2(a.pos_cur + (int64_t)kk * a.ld + in);
+          prefetch_l2(a.Frep + (int64_t)kk * ldr_ + rn);
+          if (a.update) prefetch_l2(a.Fprev + (int64_t)kk * a.ldf + rn);
+        }
+        prefetch_l2(a.mass + in);
+      }
+    }
 
     const int r = c * RPC + rl;
     const bool active = r < a.nrows;
@@ -539,8 +560,7 @@ __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArg
 // (coalesced index / weight loads, 4 gathers in flight per thread), the partial sums are combined in
 // a fixed order (lane tree, then warps in order: bit-reproducible) and thread 0 finishes the row
 // exactly like the row kernels do.
-constexpr int kLongThreads = 512;
-template <typename T, int D, bool GA>
+template <typename T, int D, bool GA, int kLongThreads>
 __global__ void __launch_bounds__(kLongThreads) k_attract_step_long(const StepArgs<T> a,
                                                                     const int* __restrict__ rows) {
   __shared__ T red[D][kLongThreads / 32];
@@ -917,21 +937,29 @@ void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int gro
 }
 
 template <typename T>
-void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong) {
+void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong,
+                              int threads) {
   if (nlong == 0) return;
   const bool ga = a.ph.general_attraction != 0;
+  auto go = [&](auto d_c, auto ga_c) {
+    constexpr int D = decltype(d_c)::value;
+    constexpr bool GA = decltype(ga_c)::value;
+    if (threads >= 512) k_attract_step_long<T, D, GA, 512><<<nlong, 512, 0, ctx->stream>>>(a, rows);
+    else k_attract_step_long<T, D, GA, 32><<<nlong, 32, 0, ctx->stream>>>(a, rows);
+  };
+  using std::integral_constant;
   if (dim == 2) {
-    if (ga) k_attract_step_long<T, 2, true><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
-    else k_attract_step_long<T, 2, false><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+    if (ga) go(integral_constant<int, 2>{}, std::true_type{});
+    else go(integral_constant<int, 2>{}, std::false_type{});
   } else {
-    if (ga) k_attract_step_long<T, 3, true><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
-    else k_attract_step_long<T, 3, false><<<nlong, kLongThreads, 0, ctx->stream>>>(a, rows);
+    if (ga) go(integral_constant<int, 3>{}, std::true_type{});
+    else go(integral_constant<int, 3>{}, std::false_type{});
   }
   GE_CUDA(cudaGetLastError());
   ctx->launches++;
 }
-template void launch_attract_step_long<double>(ge_context*, const StepArgs<double>&, int, const int*, int);
-template void launch_attract_step_long<float>(ge_context*, const StepArgs<float>&, int, const int*, int);
+template void launch_attract_step_long<double>(ge_context*, const StepArgs<double>&, int, const int*, int, int);
+template void launch_attract_step_long<float>(ge_context*, const StepArgs<float>&, int, const int*, int, int);
 
 template void launch_attract_step<double>(ge_context*, const StepArgs<double>&, int, int, bool);
 template void launch_attract_step<float>(ge_context*, const StepArgs<float>&, int, int, bool);
@@ -1054,23 +1082,32 @@ class FlatSolverT final : public FlatSolver {
     }
     // Rows far longer than the rest (power-law graphs) get a CTA each; the row kernels skip them.
     {
-      long_threshold_ = env_int("GE_LONG_ROW", 512);
-      std::vector<int> lrows;
+      // three tiers by row length: the row kernels (G lanes per row, chunked) up to long_threshold_
+      // entries, one warp per row up to 8x that, one 512-thread CTA per row beyond
+      long_threshold_ = env_int("GE_LONG_ROW", 96);
+      const int cta_threshold = 8 * long_threshold_;
+      std::vector<int> lrows, mrows;
       int64_t long_entries = 0;
       if (long_threshold_ > 0)
-        for (int r = 0; r < nrows_; ++r)
-          if (rowptr[r + 1] - rowptr[r] > long_threshold_) {
-            lrows.push_back(r);
-            long_entries += rowptr[r + 1] - rowptr[r];
+        for (int r = 0; r < nrows_; ++r) {
+          const int len = rowptr[r + 1] - rowptr[r];
+          if (len > long_threshold_) {
+            (len > cta_threshold ? lrows : mrows).push_back(r);
+            long_entries += len;
           }
+        }
       nlong_ = (int)lrows.size();
+      nmid_ = (int)mrows.size();
       if (nlong_ > 0) {
         long_rows_.alloc(ctx, lrows.size());
         long_rows_.upload(ctx, lrows.data(), lrows.size());
-      } else {
-        long_threshold_ = 0;
       }
-      const int nshort = nrows_ - nlong_;
+      if (nmid_ > 0) {
+        mid_rows_.alloc(ctx, mrows.size());
+        mid_rows_.upload(ctx, mrows.data(), mrows.size());
+      }
+      if (nlong_ + nmid_ == 0) long_threshold_ = 0;
+      const int nshort = nrows_ - nlong_ - nmid_;
       avg_deg_ = nshort > 0 ? double(lnnz - long_entries) / nshort : 0.0;
       // Gather locality after the renumbering: the mean distance |i - j| over the entries.  2-D
       // geometric graphs stay within a few hundred positions (the neighbours' coordinates are L1
@@ -1084,9 +1121,9 @@ class FlatSolverT final : public FlatSolver {
       if (std::getenv("GE_GATHER_COPY_REORDERED") == nullptr)
         gather_copy_reordered_ = mean_span_ > env_int("GE_GATHER_SPAN", 2048);
       if (std::getenv("GE_VERBOSE"))
-        std::fprintf(stderr, "[ge] flat plan rows=%d entries=%d long rows=%d (%.1f%% of the entries) "
+        std::fprintf(stderr, "[ge] flat plan rows=%d entries=%d long rows=%d+%d (%.1f%% of the entries) "
                              "avg degree of the rest %.1f mean |i-j| %.0f gather copy %d\n",
-                     nrows_, lnnz, nlong_, lnnz ? 100.0 * long_entries / lnnz : 0.0, avg_deg_, mean_span_,
+                     nrows_, lnnz, nmid_, nlong_, lnnz ? 100.0 * long_entries / lnnz : 0.0, avg_deg_, mean_span_,
                      (int)(use_gather_copy_ && (perm_.size() == 0 || gather_copy_reordered_)));
     }
     GE_CUDA(cudaStreamSynchronize(ctx->stream));  // the renumbered host arrays die with this scope
@@ -1253,7 +1290,8 @@ class FlatSolverT final : public FlatSolver {
     sa.update = update ? 1 : 0;
     sa.ph = ph_;
     sa.long_threshold = long_threshold_;
-    if ((kernel_mask_ & 2) && nlong_ > 0) launch_attract_step_long<T>(ctx, sa, dim_, long_rows_.get(), nlong_);
+    if ((kernel_mask_ & 2) && nlong_ > 0) launch_attract_step_long<T>(ctx, sa, dim_, long_rows_.get(), nlong_, 512);
+    if ((kernel_mask_ & 2) && nmid_ > 0) launch_attract_step_long<T>(ctx, sa, dim_, mid_rows_.get(), nmid_, 32);
     if (kernel_mask_ & 2) {
       // one lane per row while a 256-row chunk fits the staging buffer (fewest instructions per
       // row: measured 58-63 % of the HBM peak against 57-61 % with two lanes), else 2-8 lanes
@@ -1314,8 +1352,8 @@ class FlatSolverT final : public FlatSolver {
   bool staged_step_ = env_int("GE_STEP_STAGED", 1) != 0;
   bool gather_copy_reordered_ = env_int("GE_GATHER_COPY_REORDERED", 0) != 0;
   bool aos_valid_ = false, stepped_ = false;
-  DevBuf<int> rowptr_, J_, perm_, long_rows_;
-  int long_threshold_ = 0, nlong_ = 0;
+  DevBuf<int> rowptr_, J_, perm_, long_rows_, mid_rows_;
+  int long_threshold_ = 0, nlong_ = 0, nmid_ = 0;
   double mean_span_ = 0.0;
   std::unique_ptr<RepulsionPlan<T>> rep_;
   std::unique_ptr<RepulsionSymPlan<T>> sym_;

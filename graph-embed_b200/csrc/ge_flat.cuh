@@ -173,7 +173,8 @@ template <typename T>
 void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int group, bool ml);
 // The rows listed in `rows` (local row indices, nlong of them), one CTA each (flat physics).
 template <typename T>
-void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong);
+void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong,
+                              int threads);
 
 int group_for_degree(double avg_deg);
 

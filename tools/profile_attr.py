@@ -1,5 +1,6 @@
 """Small driver for ncu: the attraction + step kernel alone on a graph larger than L2.
-usage: python tools/profile_attr.py [n] [dim] [f64|f32] [iters]"""
+usage: python tools/profile_attr.py [n] [dim] [f64|f32] [iters] [rgg|delaunay|rmat]
+(rmat: n is the scale)"""
 import os
 import sys
 
@@ -14,7 +15,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 dim = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 prec = capi.GE_F32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else capi.GE_F64
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-A = graphs.rgg(n, 10.0, seed=11)
+kind = sys.argv[5] if len(sys.argv) > 5 else "rgg"
+A = (graphs.rgg(n, 10.0, seed=11) if kind == "rgg" else graphs.delaunay3d(n, seed=3) if kind == "delaunay"
+     else graphs.rmat(n, 16, seed=5))
 n = A.shape[0]
 os.environ["GE_REP_SYM"] = "0"
 ctx = capi.Context(0)
