@@ -92,6 +92,7 @@ struct RepSymArgs {
   const T* pos;      // [D][ld]
   const T* mass;     // [ld]  c = deg + 1 (0 on padding)
   T* S;              // [D][ld] raw sums: sum_j c_j (xi-xj)/dis^3 over every pair this plan owns
+  T* Srow;           // [D][ld] row sums of blocks swept whole by one CTA (input of k_sym_reduce)
   T* partial;        // [grid][2][D][rows_per_block] row sums of blocks shared between CTAs
   T* colpartial;     // column-side sums, one slab per block (written exactly once per launch)
   const SymBlockDesc* blocks;
@@ -101,6 +102,7 @@ struct RepSymArgs {
   int nblocks, rows_per_block;
   T eps2;
   T out_scale;       // != 0: S = sums * c_i * out_scale (the force itself); 0: raw sums
+  int accumulate;    // k_sym_reduce: add to S (a later pass over another column panel) instead of assigning
 };
 
 struct SymSegment {  // rows == columns [row0, row1); row0 a multiple of kTileJ
@@ -126,13 +128,18 @@ class RepulsionSymPlan {
 
  private:
   void init(const std::vector<SymSegment>& segments, int part, int parts);
+  struct PassDev {  // one pass over a column panel: its block list and tile references
+    DevBuf<SymBlockDesc> blocks;
+    DevBuf<SymTileRef> tiles;
+    int nblocks = 0, grid = 0;
+    long long units = 0;
+  };
   ge_context* ctx_;
-  int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0;
+  int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0, rb_ = 1024;
   int64_t ld_ = 0, reduce_len_ = 0;
   long long total_units_ = 0, pairs_ = 0;
-  DevBuf<SymBlockDesc> blocks_;
-  DevBuf<SymTileRef> tiles_;
-  DevBuf<T> partial_, colpartial_;
+  std::vector<PassDev> pass_;
+  DevBuf<T> partial_, colpartial_, srow_;
   size_t colpartial_elems_ = 0;
 };
 

@@ -20,6 +20,7 @@
 // slab of `colpartial` (every (block, tile) unit is visited exactly once per launch: no atomics,
 // bit-reproducible).  k_sym_reduce then forms  S_i = rows(i) - sum over blocks of columns(i).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(SymShape<IPT>::kThreads) k_repulsion_sym(const
       if (i < bd.row1) {
         if (whole) {
 #pragma unroll
-          for (int k = 0; k < D; ++k) a.S[(int64_t)k * a.ld + i] = fi[t][k];
+          for (int k = 0; k < D; ++k) a.Srow[(int64_t)k * a.ld + i] = fi[t][k];
         } else {
 #pragma unroll
           for (int k = 0; k < D; ++k)
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(256) k_sym_reduce(const RepSymArgs<T> a, int g
       while (c > 0 && W * c / G > U0) --c;
       if (W * c / G <= U0 && W * (c + 1) / G >= U1) {  // swept whole by one CTA
 #pragma unroll
-        for (int k = 0; k < D; ++k) acc[k] = a.S[(int64_t)k * a.ld + i];
+        for (int k = 0; k < D; ++k) acc[k] = a.Srow[(int64_t)k * a.ld + i];
       } else {
         for (long long cc = c; cc < G && W * cc / G < U1; ++cc) {
           const long long v0 = W * cc / G, v1 = W * (cc + 1) / G;
@@ -310,6 +311,10 @@ __global__ void __launch_bounds__(256) k_sym_reduce(const RepSymArgs<T> a, int g
         for (int k = 0; k < D; ++k) acc[k] -= a.colpartial[off + (int64_t)k * nc + (i - c0)];
       }
     }
+  }
+  if (a.accumulate) {  // a later pass over another column panel: add to what the earlier ones left
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] += a.S[(int64_t)k * a.ld + i];
   }
   if (a.out_scale != (T)0) {
     const T sc = a.mass[i] * a.out_scale;
@@ -344,11 +349,15 @@ size_t sym_smem(int dim, int threads) {
 
 // The triangular unit list of a set of segments: inside segment [s0, s1), block g covers rows
 // [s0 + g*RB, min(s1, s0 + (g+1)*RB)) and the column tiles from its own first row to the end of the
-// segment.  Returns the blocks clipped to units [U0, U1) of the concatenated list, and for every
-// 256-row tile of [0, ld) where its sums come from.
+// segment.  `blocks` are the blocks clipped to units [U0, U1) of the concatenated list (a rank's
+// share); every block of the triangle, in the plan or not, has a global ordinal.
+struct SymBlockFull {
+  SymBlockDesc d;   // unit0 / col_off filled per pass
+  int seg, gord;    // segment id, global ordinal of the block
+};
 struct SymLayout {
-  std::vector<SymBlockDesc> blocks;
-  std::vector<SymTileRef> tiles;
+  std::vector<SymBlockFull> blocks;
+  std::vector<int> tile_seg, tile_gord;  // per 256-row tile of [0, ld): its segment and block ordinal (-1: none)
   long long units = 0, colpartial_elems = 0, pairs = 0;
   int64_t reduce_len = 0;
 };
@@ -362,53 +371,108 @@ SymLayout sym_layout(int dim, int64_t ld, const std::vector<SymSegment>& segs, i
   }
   const long long U0 = total * part / parts, U1 = total * (part + 1) / parts;
   SymLayout L;
-  L.tiles.assign((size_t)(ld / kTileJ), SymTileRef{-1, 0, 0, 0});
+  L.tile_seg.assign((size_t)(ld / kTileJ), -1);
+  L.tile_gord.assign((size_t)(ld / kTileJ), -1);
   long long prefix = 0;
+  int gord = 0, seg_id = 0;
   for (const auto& sg : segs) {
     const int nt = seg_tiles(sg);
     const int t_seg = sg.row0 / kTileJ;  // global index of the segment's first tile
     const int nblk = (sg.row1 - sg.row0 + rb - 1) / rb;
-    const int seg_b0 = (int)L.blocks.size();
     L.reduce_len = std::max<int64_t>(L.reduce_len, (int64_t)(t_seg + nt) * kTileJ);
-    for (int g = 0; g < nblk; ++g) {
+    for (int g = 0; g < nblk; ++g, ++gord) {
       const int tf = (int)((int64_t)g * rb / kTileJ);  // first tile of the block, within the segment
       const long long b0 = prefix, b1 = prefix + (nt - tf);
       prefix = b1;
       const int row0 = sg.row0 + g * rb;
       const int row1 = (int)std::min<int64_t>(sg.row1, (int64_t)row0 + rb);
       const int bt1 = std::min(nt, tf + rb / kTileJ);  // the block's own row tiles [tf, bt1)
-      const long long lo = std::max(b0, U0), hi = std::min(b1, U1);
-      const int above = (int)L.blocks.size() - seg_b0;  // plan blocks of this segment above block g
-      int self = -1;
-      if (lo < hi) {
-        SymBlockDesc d;
-        d.row0 = row0;
-        d.row1 = row1;
-        d.t_first = t_seg + tf + (int)(lo - b0);
-        d.ntiles = (int)(hi - lo);
-        d.tile_sym0 = t_seg + (int)((row1 - sg.row0 + kTileJ - 1) / kTileJ);
-        d.col_t0 = std::max(d.t_first, d.tile_sym0);
-        d.ncols = std::max(0, d.t_first + d.ntiles - d.col_t0) * kTileJ;
-        d.unit0 = L.units;
-        d.col_off = L.colpartial_elems;
-        L.units += d.ntiles;
-        L.colpartial_elems += (long long)dim * d.ncols;
-        const long long rows = d.row1 - d.row0;
-        L.pairs += rows * (long long)(d.col_t0 - d.t_first) * kTileJ + 2 * rows * (long long)d.ncols;
-        self = (int)L.blocks.size();
-        L.blocks.push_back(d);
+      for (int t = tf; t < bt1; ++t) {
+        L.tile_seg[(size_t)t_seg + t] = seg_id;
+        L.tile_gord[(size_t)t_seg + t] = gord;
       }
-      for (int t = tf; t < bt1; ++t) L.tiles[(size_t)t_seg + t] = SymTileRef{self, seg_b0, above, 0};
+      const long long lo = std::max(b0, U0), hi = std::min(b1, U1);
+      if (lo >= hi) continue;
+      SymBlockFull f;
+      f.seg = seg_id;
+      f.gord = gord;
+      SymBlockDesc& d = f.d;
+      d.row0 = row0;
+      d.row1 = row1;
+      d.t_first = t_seg + tf + (int)(lo - b0);
+      d.ntiles = (int)(hi - lo);
+      d.tile_sym0 = t_seg + (int)((row1 - sg.row0 + kTileJ - 1) / kTileJ);
+      d.col_t0 = std::max(d.t_first, d.tile_sym0);
+      d.ncols = std::max(0, d.t_first + d.ntiles - d.col_t0) * kTileJ;
+      d.unit0 = 0;
+      d.col_off = 0;
+      L.units += d.ntiles;
+      L.colpartial_elems += (long long)dim * d.ncols;
+      const long long rows = d.row1 - d.row0;
+      L.pairs += rows * (long long)(d.col_t0 - d.t_first) * kTileJ + 2 * rows * (long long)d.ncols;
+      L.blocks.push_back(f);
     }
+    ++seg_id;
   }
   return L;
+}
+
+// One pass = the plan's blocks restricted to the column tiles [pt0, pt1): its own block list, unit
+// numbering, column-slab offsets and per-tile references.
+struct SymPass {
+  std::vector<SymBlockDesc> blocks;
+  std::vector<SymTileRef> tiles;
+  long long units = 0, colpartial_elems = 0;
+};
+SymPass sym_pass(int dim, const SymLayout& L, int pt0, int pt1) {
+  SymPass P;
+  std::vector<int> seg_of, gord_of;
+  for (const auto& f : L.blocks) {
+    const int t0 = std::max(f.d.t_first, pt0), t1 = std::min(f.d.t_first + f.d.ntiles, pt1);
+    if (t0 >= t1) continue;
+    SymBlockDesc d = f.d;
+    d.t_first = t0;
+    d.ntiles = t1 - t0;
+    d.col_t0 = std::max(d.t_first, d.tile_sym0);
+    d.ncols = std::max(0, d.t_first + d.ntiles - d.col_t0) * kTileJ;
+    d.unit0 = P.units;
+    d.col_off = P.colpartial_elems;
+    P.units += d.ntiles;
+    P.colpartial_elems += (long long)dim * d.ncols;
+    P.blocks.push_back(d);
+    seg_of.push_back(f.seg);
+    gord_of.push_back(f.gord);
+  }
+  // per row tile: the pass block that sweeps its rows, and the pass blocks of its segment above it
+  P.tiles.assign(L.tile_seg.size(), SymTileRef{-1, 0, 0, 0});
+  const int nb = (int)P.blocks.size();
+  std::vector<int> seg_first;  // first pass block of each segment (pass blocks are segment-major)
+  for (int b = 0; b < nb; ++b) {
+    if ((int)seg_first.size() <= seg_of[b]) seg_first.resize(seg_of[b] + 1, -1);
+    if (seg_first[seg_of[b]] < 0) seg_first[seg_of[b]] = b;
+  }
+  int cursor = 0;  // tiles ascend with (segment, block ordinal): one forward scan over the blocks
+  for (size_t t = 0; t < P.tiles.size(); ++t) {
+    const int sg = L.tile_seg[t], go = L.tile_gord[t];
+    if (sg < 0) continue;
+    while (cursor < nb && (seg_of[cursor] < sg || (seg_of[cursor] == sg && gord_of[cursor] < go))) ++cursor;
+    const int first = (sg < (int)seg_first.size() && seg_first[sg] >= 0) ? seg_first[sg] : cursor;
+    SymTileRef r;
+    r.row_block = (cursor < nb && seg_of[cursor] == sg && gord_of[cursor] == go) ? cursor : -1;
+    r.col_b0 = first;
+    r.col_n = std::max(0, cursor - first);
+    r.pad = 0;
+    P.tiles[t] = r;
+  }
+  return P;
 }
 }  // namespace
 
 void sym_share(int64_t ld, int part, int parts, std::vector<int>& out) {
   const SymLayout L = sym_layout(2, ld, {SymSegment{0, (int)ld}}, 1024, part, parts);
   out.clear();
-  for (const auto& d : L.blocks) {
+  for (const auto& f : L.blocks) {
+    const SymBlockDesc& d = f.d;
     const int v[5] = {d.row0, d.row1, d.t_first, d.ntiles, d.tile_sym0};
     out.insert(out.end(), v, v + 5);
   }
@@ -417,8 +481,11 @@ void sym_share(int64_t ld, int part, int parts, std::vector<int>& out) {
 template <typename T>
 double RepulsionSymPlan<T>::scratch_bytes(int dim, int64_t ld, int parts) {
   const int rb = 1024;  // both launch shapes (512 x 2, 256 x 4) cover 1024 rows per block
-  // the triangle holds ~ ld^2 / (2 rb) column entries per dimension, shared out over the parts
-  return 1.05 * double(dim) * sizeof(T) * double(ld) * double(ld) / (2.0 * rb) / parts + 1e6;
+  // the triangle holds ~ ld^2 / (2 rb) column entries per dimension, shared out over the parts; the
+  // plan cuts the sweep into passes over column panels so that one pass stays under the cap
+  const double all = 1.05 * double(dim) * sizeof(T) * double(ld) * double(ld) / (2.0 * rb) / parts + 1e6;
+  const double cap = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 1024);
+  return std::min(all, 1.3 * cap + 1e6) + double(dim) * sizeof(T) * double(ld);
 }
 
 template <typename T>
@@ -454,56 +521,103 @@ void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part
   for (const auto& sg : segments)
     GE_REQUIRE(sg.row0 % kTileJ == 0 && sg.row0 <= sg.row1 && sg.row1 <= ld_, "bad segment");
   SymLayout L = sym_layout(dim_, ld_, segments, rb, part, parts);
-  nblocks_ = (int)L.blocks.size();
-  total_units_ = L.units;
   pairs_ = L.pairs;
   reduce_len_ = parts > 1 ? ld_ : L.reduce_len;  // multi-rank: every row's sums enter the reduce-scatter
-  grid_ = (int)std::min<long long>((long long)ctx->sm_count * occ, std::max<long long>(L.units, 1));
-  blocks_.alloc(ctx, std::max<size_t>(L.blocks.size(), 1));
-  blocks_.upload(ctx, L.blocks.data(), L.blocks.size());
-  tiles_.alloc(ctx, std::max<size_t>(L.tiles.size(), 1));
-  tiles_.upload(ctx, L.tiles.data(), L.tiles.size());
+  rb_ = rb;
+  // The column-side slabs hold n^2 / (2 rb) entries per dimension.  When that exceeds the cap the
+  // sweep is cut into passes over column panels that reuse one scratch buffer (same kernels, same
+  // pairs; k_sym_reduce adds each pass's sums to the previous ones), so memory stays bounded for
+  // any n instead of falling back to the ordered sweep.
+  const double cap_elems = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 1024) / sizeof(T);
+  int npass = (int)std::min<double>(64.0, std::ceil(std::max(1.0, double(L.colpartial_elems) / cap_elems)));
+  npass = std::max(1, env_int("GE_SYM_PASSES", npass));
+  const int ntile = (int)(ld_ / kTileJ);
+  long long max_units = 1, max_col = 1;
+  size_t max_blocks = 1;
+  std::vector<SymPass> passes;
+  // equal numbers of column-side entries per pass: the triangle's columns fill linearly, so the
+  // panel boundaries go with the square root
+  for (int q = 0; q < npass; ++q) {
+    const int pt0 = (int)std::floor(ntile * std::sqrt(double(q) / npass));
+    const int pt1 = q == npass - 1 ? ntile : (int)std::floor(ntile * std::sqrt(double(q + 1) / npass));
+    if (pt1 <= pt0) continue;
+    passes.push_back(sym_pass(dim_, L, pt0, pt1));
+    if (passes.back().units == 0) {
+      passes.pop_back();
+      continue;
+    }
+    max_units = std::max(max_units, passes.back().units);
+    max_col = std::max(max_col, passes.back().colpartial_elems);
+    max_blocks = std::max(max_blocks, passes.back().blocks.size());
+  }
+  grid_ = (int)std::min<long long>((long long)ctx->sm_count * occ, max_units);
+  pass_.clear();
+  for (auto& P : passes) {
+    PassDev pd;
+    pd.nblocks = (int)P.blocks.size();
+    pd.units = P.units;
+    pd.grid = (int)std::min<long long>(grid_, std::max<long long>(P.units, 1));
+    pd.blocks.alloc(ctx, std::max<size_t>(P.blocks.size(), 1));
+    pd.blocks.upload(ctx, P.blocks.data(), P.blocks.size());
+    pd.tiles.alloc(ctx, std::max<size_t>(P.tiles.size(), 1));
+    pd.tiles.upload(ctx, P.tiles.data(), P.tiles.size());
+    pass_.push_back(std::move(pd));
+  }
+  total_units_ = L.units;
+  nblocks_ = (int)L.blocks.size();
   partial_.alloc(ctx, (size_t)grid_ * 2 * dim_ * rb);
-  colpartial_elems_ = (size_t)std::max<long long>(L.colpartial_elems, 1);
+  srow_.alloc(ctx, (size_t)dim_ * ld_);
+  colpartial_elems_ = (size_t)max_col;
   colpartial_.alloc(ctx, colpartial_elems_);
   GE_CUDA(cudaStreamSynchronize(ctx->stream));
   if (std::getenv("GE_VERBOSE"))
     std::fprintf(stderr,
                  "[ge] symmetric repulsion plan: segments=%zu threads=%d ipt=%d cg=%d grid=%d (occ %d) "
-                 "blocks=%d units=%lld column scratch %.1f MB\n",
-                 segments.size(), threads_, ipt_, cg_, grid_, occ, nblocks_, total_units_,
-                 double(L.colpartial_elems) * sizeof(T) / 1e6);
+                 "blocks=%d units=%lld passes=%zu column scratch %.1f MB (one pass would need %.1f MB)\n",
+                 segments.size(), threads_, ipt_, cg_, grid_, occ, nblocks_, total_units_, pass_.size(),
+                 double(max_col) * sizeof(T) / 1e6, double(L.colpartial_elems) * sizeof(T) / 1e6);
 }
 
 template <typename T>
 void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2, T out_scale) {
   if (colpartial_.size() == 0) colpartial_.alloc(ctx_, colpartial_elems_);
-  RepSymArgs<T> a;
-  a.pos = pos;
-  a.mass = mass;
-  a.S = S;
-  a.partial = partial_.get();
-  a.colpartial = colpartial_.get();
-  a.blocks = blocks_.get();
-  a.tiles = tiles_.get();
-  a.ld = ld_;
-  a.total_units = std::max<long long>(total_units_, 1);
-  a.nblocks = nblocks_;
-  a.rows_per_block = threads_ * ipt_;
-  a.eps2 = eps2;
-  a.out_scale = out_scale;
-  if (nblocks_ > 0 && total_units_ > 0) {
-    void* args[] = {(void*)&a};
-    GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_), dim3(grid_), dim3(threads_), args,
-                             sym_smem<T>(dim_, threads_), ctx_->stream));
-    ctx_->launches++;
+  bool first = true;
+  for (size_t q = 0; q < pass_.size(); ++q) {
+    const PassDev& pd = pass_[q];
+    const bool last = q + 1 == pass_.size();
+    RepSymArgs<T> a;
+    a.pos = pos;
+    a.mass = mass;
+    a.S = S;
+    a.Srow = srow_.get();
+    a.partial = partial_.get();
+    a.colpartial = colpartial_.get();
+    a.blocks = pd.blocks.get();
+    a.tiles = pd.tiles.get();
+    a.ld = ld_;
+    a.total_units = std::max<long long>(pd.units, 1);
+    a.nblocks = pd.nblocks;
+    a.rows_per_block = rb_;
+    a.eps2 = eps2;
+    a.out_scale = last ? out_scale : (T)0;
+    a.accumulate = first ? 0 : 1;
+    if (pd.nblocks > 0 && pd.units > 0) {
+      void* args[] = {(void*)&a};
+      GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_), dim3(pd.grid), dim3(threads_), args,
+                               sym_smem<T>(dim_, threads_), ctx_->stream));
+      ctx_->launches++;
+    }
+    if (reduce_len_ > 0) {
+      const unsigned rgrid = (unsigned)((reduce_len_ + 255) / 256);
+      if (dim_ == 2) k_sym_reduce<T, 2><<<rgrid, 256, 0, ctx_->stream>>>(a, pd.grid, reduce_len_);
+      else k_sym_reduce<T, 3><<<rgrid, 256, 0, ctx_->stream>>>(a, pd.grid, reduce_len_);
+      GE_CUDA(cudaGetLastError());
+      ctx_->launches++;
+    }
+    first = false;
   }
-  if (reduce_len_ > 0) {
-    const unsigned rgrid = (unsigned)((reduce_len_ + 255) / 256);
-    if (dim_ == 2) k_sym_reduce<T, 2><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_, reduce_len_);
-    else k_sym_reduce<T, 3><<<rgrid, 256, 0, ctx_->stream>>>(a, grid_, reduce_len_);
-    GE_CUDA(cudaGetLastError());
-    ctx_->launches++;
+  if (pass_.empty() && reduce_len_ > 0) {  // a rank without any pair: its sums are zero
+    GE_CUDA(cudaMemsetAsync(S, 0, sizeof(T) * (size_t)dim_ * ld_, ctx_->stream));
   }
 }
 

@@ -86,6 +86,38 @@ def test_momentum_conservation(ctx, capi, graphs, sym):
     assert np.abs(F.sum(0)).max() < 1e-9 * np.abs(F).sum(0).max()
 
 
+@pytest.mark.parametrize("passes", [2, 3, 7])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_column_panel_passes(ctx, capi, oracle, graphs, sym, passes, dim):
+    """Large graphs cut the sweep into passes over column panels that reuse one scratch buffer (the
+    column-side slabs grow with n^2); forced here on a 5-block graph: forces against the oracle,
+    and the same positions as the one-pass plan up to summation order, also on rank plans and on
+    a segmented (per-aggregate) sweep."""
+    A = graphs.rgg(5003, 10.0, seed=3)
+    n = A.shape[0]
+    x0 = capi.reference_uniform(11, n * dim).reshape(n, dim)
+    F_ref, S = oracle.flat_forces(A, dim, x0)
+    sym.setenv("GE_SYM_PASSES", "1")
+    one = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=2))
+    sym.setenv("GE_SYM_PASSES", str(passes))
+    F = ctx.flat_forces(A, dim, x0, capi.flat_params(), path=1)
+    assert force_error(F, F_ref, S).max() < TOL_F64
+    got = ctx.flat_forceatlas(A, dim, x0, capi.flat_params(iterations=2))
+    assert np.abs(got - one).max() < 1e-11 * np.abs(one).max()
+    # the large-aggregate tier of the per-aggregate solver runs the same plan over segments
+    sym.setenv("GE_CTA_MAX", "40")
+    sym.setenv("GE_ML_SYM_MIN_MPAIRS", "0")
+    As, Ps = graphs.coarsen(graphs.rgg(6000, 10.0, seed=3), 0.004, min_coarse=10, max_levels=1)
+    Al, P = As[0], Ps[0]
+    assert np.diff(P.indptr).max() > 300
+    m = P.shape[0]
+    cA = np.random.default_rng(1).normal(size=(m, dim))
+    x = capi.reference_uniform(3, Al.shape[0] * dim).reshape(-1, dim)
+    _, Fm_ref, Sm = oracle.multilevel_run(Al, P, cA, np.ones(m), dim, x, oracle.Params(iterations=1), forces_iter=0)
+    Fm = ctx.multilevel_forces(Al, P, cA, x, dim, capi.multilevel_params())
+    assert force_error(Fm, Fm_ref, Sm).max() < TOL_F64
+
+
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_multi_rank_plans_on_one_gpu(ctx, capi, graphs, sym, world, dim):
