@@ -484,7 +484,7 @@ double RepulsionSymPlan<T>::scratch_bytes(int dim, int64_t ld, int parts) {
   // the triangle holds ~ ld^2 / (2 rb) column entries per dimension, shared out over the parts; the
   // plan cuts the sweep into passes over column panels so that one pass stays under the cap
   const double all = 1.05 * double(dim) * sizeof(T) * double(ld) * double(ld) / (2.0 * rb) / parts + 1e6;
-  const double cap = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 1024);
+  const double cap = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 2048);
   return std::min(all, 1.3 * cap + 1e6) + double(dim) * sizeof(T) * double(ld);
 }
 
@@ -528,7 +528,7 @@ void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part
   // sweep is cut into passes over column panels that reuse one scratch buffer (same kernels, same
   // pairs; k_sym_reduce adds each pass's sums to the previous ones), so memory stays bounded for
   // any n instead of falling back to the ordered sweep.
-  const double cap_elems = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 1024) / sizeof(T);
+  const double cap_elems = 1048576.0 * env_int("GE_SYM_SCRATCH_MB", 2048) / sizeof(T);
   int npass = (int)std::min<double>(64.0, std::ceil(std::max(1.0, double(L.colpartial_elems) / cap_elems)));
   npass = std::max(1, env_int("GE_SYM_PASSES", npass));
   const int ntile = (int)(ld_ / kTileJ);
