@@ -73,6 +73,7 @@ SYMBOLS = [
     "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
     "ge_flat_symmetric_share", "ge_galerkin", "ge_level_radii_device",
     "ge_context_create_multi", "ge_context_device_count",
+    "ge_flat_symmetric_pass_share", "ge_embed_aggregate_ranges",
 ]
 
 _lib = None
@@ -345,6 +346,29 @@ def symmetric_share(ld, rank, world):
     buf = np.zeros(max(nb, 1) * 5, dtype=np.int32)
     L.ge_flat_symmetric_share(int(ld), int(rank), int(world), nb, buf.ctypes.data_as(C.c_void_p))
     return [tuple(int(v) for v in buf[5 * i:5 * i + 5]) for i in range(nb)]
+
+
+def symmetric_pass_share(ld, rank, world, npass, q):
+    """ge_flat_symmetric_pass_share -> [(row0, row1, tile_first, ntiles, tile_sym0)] (host only)."""
+    L = lib()
+    L.ge_flat_symmetric_pass_share.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_void_p]
+    nb = L.ge_flat_symmetric_pass_share(int(ld), int(rank), int(world), int(npass), int(q), 0, None)
+    if nb < 0:
+        raise ValueError("bad arguments")
+    buf = np.zeros(max(nb, 1) * 5, dtype=np.int32)
+    L.ge_flat_symmetric_pass_share(int(ld), int(rank), int(world), int(npass), int(q), nb,
+                                   buf.ctypes.data_as(C.c_void_p))
+    return [tuple(int(v) for v in buf[5 * i:5 * i + 5]) for i in range(nb)]
+
+
+def embed_aggregate_ranges(A, P_T, ndev):
+    """ge_embed_aggregate_ranges -> (cuts[ndev + 1], ordered pairs per iteration) (host only)."""
+    a, p = CsrView(A), CsrView(P_T, with_data=False)
+    cuts = np.zeros(ndev + 1, dtype=np.int32)
+    pairs = C.c_double()
+    _check(lib().ge_embed_aggregate_ranges(a.ref(), p.ref(), int(ndev), _ptr(cuts, _pi), C.byref(pairs)))
+    return cuts, pairs.value
 
 
 class FlatPlan:

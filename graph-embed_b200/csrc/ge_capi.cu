@@ -434,6 +434,33 @@ void flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords, const
   s->download_coords(coords);
 }
 
+// Cost-balanced contiguous aggregate ranges, one per device: cost(a) = s_a^2 ordered pairs + the CSR
+// entries of its members' rows.  cuts: N + 1 boundaries, cuts[0] = 0,
+// cuts[N] = m.  Returns the ordered intra-aggregate pairs per iteration of the level.
+double aggregate_ranges(const ge_csr& A, const ge_csr& P, int N, std::vector<int>& cuts) {
+  const int m = P.rows;
+  std::vector<double> cost((size_t)m + 1, 0.0);
+  double pairs = 0.0;
+  for (int a = 0; a < m; ++a) {
+    const double s = P.indptr[a + 1] - P.indptr[a];
+    double nnz = 0.0;
+    for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
+      nnz += A.indptr[P.indices[c] + 1] - A.indptr[P.indices[c]];
+    pairs += s * (s - 1);
+    cost[a + 1] = cost[a] + s * s + nnz;
+  }
+  cuts.assign(N + 1, 0);
+  int prev = 0;
+  for (int d = 0; d < N; ++d) {
+    const double target = cost[m] * (d + 1) / N;
+    int cut = d == N - 1 ? m : (int)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
+    cut = std::max(prev, std::min(cut, m));
+    cuts[d + 1] = cut;
+    prev = cut;
+  }
+  return pairs;
+}
+
 // partition::embed on one device or, with a multi-device context, with the large levels sharded by
 // aggregates (aggregates are independent, include/forceatlas.hpp:340-341).
 struct EmbedRun {
@@ -480,30 +507,15 @@ struct EmbedRun {
     const char* e = std::getenv("GE_SHARD_MIN_MPAIRS");
     const double min_pairs = 1e6 * (e ? std::atof(e) : 200.0);
     for (int l = 0; l < L; ++l) {
-      const ge_csr& P = Ps[l];
-      const int m = P.rows;
-      devs[0].a1[l] = m;
+      devs[0].a1[l] = Ps[l].rows;
       if (N == 1) continue;
-      std::vector<double> cost((size_t)m + 1, 0.0);
-      double pairs = 0.0;
-      for (int a = 0; a < m; ++a) {
-        const double s = P.indptr[a + 1] - P.indptr[a];
-        double nnz = 0.0;
-        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
-          nnz += As[l].indptr[P.indices[c] + 1] - As[l].indptr[P.indices[c]];
-        pairs += s * (s - 1);
-        cost[a + 1] = cost[a] + s * s + nnz;
-      }
+      std::vector<int> cuts;
+      const double pairs = aggregate_ranges(As[l], Ps[l], N, cuts);
       if (pairs < min_pairs) continue;
       sharded[l] = 1;
-      int prev = 0;
       for (int d = 0; d < N; ++d) {
-        const double target = cost[m] * (d + 1) / N;
-        int cut = d == N - 1 ? m : (int)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
-        cut = std::max(prev, std::min(cut, m));
-        devs[d].a0[l] = prev;
-        devs[d].a1[l] = cut;
-        prev = cut;
+        devs[d].a0[l] = cuts[d];
+        devs[d].a1[l] = cuts[d + 1];
       }
     }
   }
@@ -1170,6 +1182,30 @@ int32_t ge_flat_symmetric_share(int64_t ld, int32_t rank, int32_t world, int32_t
   if (blocks)
     for (int i = 0; i < std::min(nb, (int)capacity) * 5; ++i) blocks[i] = v[i];
   return nb;
+}
+int32_t ge_flat_symmetric_pass_share(int64_t ld, int32_t rank, int32_t world, int32_t npass, int32_t pass,
+                                     int32_t capacity, int32_t* blocks) {
+  if (ld <= 0 || ld % 256 || world < 1 || rank < 0 || rank >= world || npass < 1 || pass < 0 || pass >= npass)
+    return -1;
+  std::vector<int> v;
+  sym_pass_share(ld, rank, world, npass, pass, v);
+  const int nb = (int)v.size() / 5;
+  if (blocks)
+    for (int i = 0; i < std::min(nb, (int)capacity) * 5; ++i) blocks[i] = v[i];
+  return nb;
+}
+ge_status ge_embed_aggregate_ranges(const ge_csr* A, const ge_csr* P_T, int32_t ndev, int32_t* cuts,
+                                    double* pairs_per_iteration) {
+  return guarded([&] {
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(ndev >= 1 && cuts != nullptr, "bad argument");
+    GE_REQUIRE(P_T->cols == A->rows && P_T->indptr[P_T->rows] == A->rows, "P_T must list every vertex once");
+    std::vector<int> c;
+    const double pairs = aggregate_ranges(*A, *P_T, ndev, c);
+    for (int d = 0; d <= ndev; ++d) cuts[d] = c[d];
+    if (pairs_per_iteration) *pairs_per_iteration = pairs;
+  });
 }
 int32_t ge_flat_plan_is_symmetric(const ge_flat_plan* plan) { return plan->solver->symmetric() ? 1 : 0; }
 void* ge_flat_plan_pair_sums(ge_flat_plan* plan) { return plan->solver->pair_sums(); }

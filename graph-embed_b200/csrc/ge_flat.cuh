@@ -145,6 +145,8 @@ class RepulsionSymPlan {
 
 // The (row0, row1, tile_first, ntiles, tile_sym0) quintuples of share `part` of `parts` (host).
 void sym_share(int64_t ld, int part, int parts, std::vector<int>& out);
+// The same for pass q of npass column-panel passes of that share (RepulsionSymPlan's cut).
+void sym_pass_share(int64_t ld, int part, int parts, int npass, int q, std::vector<int>& out);
 
 template <typename T>
 struct StepArgs {

@@ -30,6 +30,8 @@
 
 namespace ge {
 
+void sym_pass_bounds(int ntile, int npass, int q, int& pt0, int& pt1);
+
 namespace {
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 }  // namespace
@@ -468,6 +470,26 @@ SymPass sym_pass(int dim, const SymLayout& L, int pt0, int pt1) {
 }
 }  // namespace
 
+// Column-tile panel [pt0, pt1) of pass q of npass: equal numbers of column-side entries per pass (the
+// triangle's columns fill linearly, so the boundaries go with the square root).
+void sym_pass_bounds(int ntile, int npass, int q, int& pt0, int& pt1) {
+  pt0 = (int)std::floor(ntile * std::sqrt(double(q) / npass));
+  pt1 = q == npass - 1 ? ntile : (int)std::floor(ntile * std::sqrt(double(q + 1) / npass));
+}
+
+void sym_pass_share(int64_t ld, int part, int parts, int npass, int q, std::vector<int>& out) {
+  const SymLayout L = sym_layout(2, ld, {SymSegment{0, (int)ld}}, 1024, part, parts);
+  int pt0, pt1;
+  sym_pass_bounds((int)(ld / kTileJ), npass, q, pt0, pt1);
+  out.clear();
+  if (pt1 <= pt0) return;
+  const SymPass P = sym_pass(2, L, pt0, pt1);
+  for (const auto& d : P.blocks) {
+    const int v[5] = {d.row0, d.row1, d.t_first, d.ntiles, d.tile_sym0};
+    out.insert(out.end(), v, v + 5);
+  }
+}
+
 void sym_share(int64_t ld, int part, int parts, std::vector<int>& out) {
   const SymLayout L = sym_layout(2, ld, {SymSegment{0, (int)ld}}, 1024, part, parts);
   out.clear();
@@ -538,8 +560,8 @@ void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part
   // equal numbers of column-side entries per pass: the triangle's columns fill linearly, so the
   // panel boundaries go with the square root
   for (int q = 0; q < npass; ++q) {
-    const int pt0 = (int)std::floor(ntile * std::sqrt(double(q) / npass));
-    const int pt1 = q == npass - 1 ? ntile : (int)std::floor(ntile * std::sqrt(double(q + 1) / npass));
+    int pt0, pt1;
+    sym_pass_bounds(ntile, npass, q, pt0, pt1);
     if (pt1 <= pt0) continue;
     passes.push_back(sym_pass(dim_, L, pt0, pt1));
     if (passes.back().units == 0) {

@@ -242,6 +242,15 @@ ge_status ge_flat_plan_create_symmetric(ge_context* ctx, const ge_csr* A, int di
  * tile); returns the number of quintuples (at most `capacity` are written), -1 on bad arguments. */
 int32_t ge_flat_symmetric_share(int64_t ld, int32_t rank, int32_t world, int32_t capacity,
                                 int32_t* blocks);
+/* Host-only: the same for pass `pass` of `npass` column-panel passes of that share (large graphs cut
+ * the sweep into passes that reuse one column-side scratch buffer). */
+int32_t ge_flat_symmetric_pass_share(int64_t ld, int32_t rank, int32_t world, int32_t npass, int32_t pass,
+                                     int32_t capacity, int32_t* blocks);
+/* Host-only: how ge_embed on an ndev-device context cuts one level into contiguous aggregate ranges
+ * of (nearly) equal cost (s^2 ordered pairs + the members' CSR entries): cuts[0..ndev], cuts[0] = 0,
+ * cuts[ndev] = P_T->rows. */
+ge_status ge_embed_aggregate_ranges(const ge_csr* A, const ge_csr* P_T, int32_t ndev, int32_t* cuts,
+                                    double* pairs_per_iteration);
 /* 1 if the plan evaluates unordered pairs (ge_flat_plan_create chooses this for whole-graph plans
  * on large graphs), 0 for the ordered row-block sweep. */
 int32_t ge_flat_plan_is_symmetric(const ge_flat_plan* plan);

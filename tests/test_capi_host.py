@@ -94,3 +94,53 @@ def test_symmetric_share_matches_python_mirror(capi):
         for world in (1, 2, 4, 8):
             for rank in range(world):
                 assert capi.symmetric_share(ld, rank, world) == sharding.pair_share(ld, world, rank)
+
+
+def _units(blocks):
+    """(row block, column tile) units of a share, as a set of (row0, tile)."""
+    out = set()
+    for row0, row1, tf, nt, tsym in blocks:
+        for t in range(tf, tf + nt):
+            assert (row0, t) not in out
+            out.add((row0, t))
+    return out
+
+
+def test_column_panel_passes_cover_every_unit_once(capi):
+    """Large graphs cut the symmetric sweep into passes over column panels (one scratch buffer
+    reused): over all passes every (row block, column tile) unit of the rank's share appears
+    exactly once, tiles stay inside their panel, and panels are ordered."""
+    for ld in (1024, 5120, 500_224):
+        for world in (1, 4):
+            for rank in range(world):
+                whole = _units(capi.symmetric_share(ld, rank, world))
+                for npass in (1, 2, 7, 30):
+                    seen, last_hi = set(), 0
+                    for q in range(npass):
+                        blocks = capi.symmetric_pass_share(ld, rank, world, npass, q)
+                        u = _units(blocks)
+                        assert not (u & seen)
+                        seen |= u
+                        if u:
+                            lo, hi = min(t for _, t in u), max(t for _, t in u)
+                            assert lo >= last_hi          # panels do not overlap and ascend
+                            last_hi = hi + 1
+                    assert seen == whole, (ld, world, rank, npass)
+
+
+def test_embed_aggregate_ranges_are_contiguous_and_balanced(capi, graphs):
+    """How ge_embed on an N-device context shares out a level: contiguous aggregate ranges that
+    cover every aggregate once, each within one aggregate's cost of the mean."""
+    A = graphs.rmat(13, 16, seed=2)
+    As, Ps = graphs.coarsen(A, 0.25, min_coarse=50, max_levels=2)
+    for l, P in enumerate(Ps):
+        s = np.diff(P.indptr).astype(np.float64)
+        row_nnz = np.diff(As[l].indptr).astype(np.float64)
+        member_nnz = np.add.reduceat(row_nnz[P.indices], P.indptr[:-1])
+        cost = s * s + member_nnz
+        for ndev in (1, 2, 3, 8):
+            cuts, pairs = capi.embed_aggregate_ranges(As[l], P, ndev)
+            assert cuts[0] == 0 and cuts[-1] == P.shape[0] and (np.diff(cuts) >= 0).all()
+            assert pairs == float((s * (s - 1)).sum())
+            per = [cost[cuts[d]:cuts[d + 1]].sum() for d in range(ndev)]
+            assert max(per) <= cost.sum() / ndev + cost.max() + 1e-9
