@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -982,6 +983,15 @@ class FlatSolverT final : public FlatSolver {
               int part, int parts)
       : n_(A.rows), dim_(dim), rb_(rb), re_(re), parts_(parts) {
     ctx = c;
+    const bool verbose_ctor = std::getenv("GE_VERBOSE_PLAN") != nullptr;
+    double t_ctor = now_ms();
+    auto lap = [&](const char* what) {
+      if (!verbose_ctor) return;
+      cudaStreamSynchronize(ctx->stream);
+      const double t = now_ms();
+      std::fprintf(stderr, "[ge] flat plan ctor dev %d %-18s %8.3f ms\n", ctx->device, what, t - t_ctor);
+      t_ctor = t;
+    };
     ph_ = make_physics<T>(p);
     ld_ = round_up(std::max(n_, 1), kTileJ);
     nrows_ = re_ - rb_;
@@ -1038,18 +1048,34 @@ class FlatSolverT final : public FlatSolver {
       perm_.upload(ctx, perm.data(), n_);
     }
 
+    lap("renumbering");
     // Vertex masses need every row's degree (include/forceatlas.hpp:127-140); rows outside the
     // owned block contribute nothing else.
     std::vector<double> deg(n_);
     const bool weighted = p.use_weights && A.data != nullptr;
-    for (int i = 0; i < n_; ++i) {
-      double s = 0.0;
-      if (weighted) {
-        for (int e = I[i]; e < I[i + 1]; ++e) s += Dw[e];
+    {
+      // row sums in CSR order (bit-identical whatever the thread count: rows are independent); a
+      // few host threads on large graphs, where this pass is milliseconds of every plan creation
+      auto rows = [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+          double s = 0.0;
+          if (weighted) {
+            for (int e = I[i]; e < I[i + 1]; ++e) s += Dw[e];
+          } else {
+            s = 1.0 * (I[i + 1] - I[i]);
+          }
+          deg[i] = s;
+        }
+      };
+      const int nt = (weighted && I[n_] > (1 << 20)) ? 8 : 1;
+      if (nt == 1) {
+        rows(0, n_);
       } else {
-        s = 1.0 * (I[i + 1] - I[i]);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t)
+          pool.emplace_back(rows, (int)((int64_t)n_ * t / nt), (int)((int64_t)n_ * (t + 1) / nt));
+        for (auto& th : pool) th.join();
       }
-      deg[i] = s;
     }
     DevBuf<double> d_deg(ctx, std::max(n_, 1));
     d_deg.upload(ctx, deg.data(), n_);
@@ -1058,6 +1084,7 @@ class FlatSolverT final : public FlatSolver {
         d_deg.get(), n_, ld_, NM, mass_.get());
     ctx->launches++;
 
+    lap("masses");
     // owned CSR rows, re-based to local entry offsets
     const int e0 = I[rb_], e1 = I[re_];
     const int lnnz = e1 - e0;
@@ -1080,6 +1107,7 @@ class FlatSolverT final : public FlatSolver {
         W_.upload(ctx, w.data(), lnnz);
       }
     }
+    lap("graph upload");
     // Rows far longer than the rest (power-law graphs) get a CTA each; the row kernels skip them.
     {
       // three tiers by row length: the row kernels (G lanes per row, chunked) up to long_threshold_
@@ -1115,9 +1143,11 @@ class FlatSolverT final : public FlatSolver {
       // ~9000, R-MAT: ~26000), every gathered coordinate then costs a 32-byte L2 sector per
       // dimension, and the interleaved copy (one sector per neighbour) pays for its extra write.
       double span = 0.0;
-      for (int r = 0; r < nrows_; ++r)
-        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) span += std::abs((rb_ + r) - J[e0 + e]);
-      mean_span_ = lnnz > 0 ? span / lnnz : 0.0;
+      int64_t sampled = 0;
+      const int stride = nrows_ > (1 << 16) ? 16 : 1;  // a sample of the rows is enough for a threshold
+      for (int r = 0; r < nrows_; r += stride)
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e, ++sampled) span += std::abs((rb_ + r) - J[e0 + e]);
+      mean_span_ = sampled > 0 ? span / sampled : 0.0;
       if (std::getenv("GE_GATHER_COPY_REORDERED") == nullptr)
         gather_copy_reordered_ = mean_span_ > env_int("GE_GATHER_SPAN", 2048);
       if (std::getenv("GE_VERBOSE"))
@@ -1128,6 +1158,7 @@ class FlatSolverT final : public FlatSolver {
     }
     GE_CUDA(cudaStreamSynchronize(ctx->stream));  // the renumbered host arrays die with this scope
 
+    lap("row tiers + span");
     aos_[0].alloc(ctx, (size_t)gather_dp() * ld_);
     aos_[1].alloc(ctx, (size_t)gather_dp() * ld_);
     own0_.alloc(ctx, (size_t)dim_ * ld_);
@@ -1142,6 +1173,7 @@ class FlatSolverT final : public FlatSolver {
     Fprev_.zero(ctx->stream);
     stage_.alloc(ctx, (size_t)std::max(n_, 1) * dim_);
 
+    lap("buffers");
     // Whole-graph plans on large graphs evaluate every unordered pair once (ge_flat_sym.cu); the
     // column-side scratch grows with n^2 / 2048, so very large graphs (and row-block plans, whose
     // pairs are not closed under transposition) keep the ordered sweep.
@@ -1170,6 +1202,7 @@ class FlatSolverT final : public FlatSolver {
     }
     for (auto& e : ev_) GE_CUDA(cudaEventCreate(&e));
     GE_CUDA(cudaStreamSynchronize(ctx->stream));
+    lap("repulsion plan");
   }
   ~FlatSolverT() override {
     for (auto& e : ev_)

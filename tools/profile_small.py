@@ -27,6 +27,19 @@ if mode == "k3":
         t = time.time()
         ctx.flat_forceatlas(Ac, 2, x0, capi.flat_params(iterations=iters))
         print("K3 %d iters: %.3f ms -> %.3f us/iter" % (iters, 1e3 * (time.time() - t), 1e6 * (time.time() - t) / iters))
+elif mode == "k3dense":
+    # the (nearly) complete coarsest graph of a power-law hierarchy: dense variant of the cluster kernel
+    import time
+    import scipy.sparse as sp
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    rng = np.random.default_rng(3)
+    M = rng.random((54, 54))
+    Ac = graphs.canonical(sp.csr_matrix(M + M.T))
+    x0 = capi.reference_uniform(1, 54 * 3).reshape(-1, 3)
+    for rep in range(2):
+        t = time.time()
+        ctx.flat_forceatlas(Ac, 3, x0, capi.flat_params(iterations=iters))
+        print("K3 dense n=54 d=3 %d iters: %.3f us/iter" % (iters, 1e6 * (time.time() - t) / iters))
 elif mode == "k3sweep":
     import time
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
