@@ -228,22 +228,12 @@ def _embed_properties(ctx, capi, As, Ps, dim):
 @pytest.mark.parametrize("name", ["rmat16_d3", "delaunay200k_d3"])
 def test_config3_config5_shapes_reduced(ctx, capi, graphs, name):
     """BASELINE configs 3 (R-MAT, d = 3, coarsening 0.25) and 5 (3-D Delaunay mesh, d = 3,
-    coarsening 0.125) at reduced size; the full sizes run under GE_FULL_CONFIGS=1 below."""
+    coarsening 0.125) at reduced size on the stand-in generator; the reference partitioner's own
+    hierarchies for both configs run in tests/test_gpu_refhier.py."""
     if name == "rmat16_d3":
         As, Ps = graphs.coarsen(graphs.rmat(16, 16, seed=1), 0.25, min_coarse=64)
     else:
         As, Ps = graphs.coarsen(graphs.delaunay3d(200_000, seed=1), 0.125, min_coarse=64)
-    _embed_properties(ctx, capi, As, Ps, 3)
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("GE_FULL_CONFIGS"),
-                    reason="full-size configs 3 / 5 take minutes of host-side graph generation; set GE_FULL_CONFIGS=1")
-@pytest.mark.parametrize("name", ["config3", "config5"])
-def test_config3_config5_full_size(ctx, capi, graphs, name):
-    if name == "config3":   # R-MAT scale 20, edge factor 16, largest component: 646k vertices, 31M entries
-        As, Ps = graphs.coarsen(graphs.rmat(20, 16, seed=1), 0.25, min_coarse=64)
-    else:                   # Delaunay tetrahedralisation of 4M points: ~62M entries
-        As, Ps = graphs.coarsen(graphs.delaunay3d(4_000_000, seed=1), 0.125, min_coarse=64)
     _embed_properties(ctx, capi, As, Ps, 3)
 
 
