@@ -275,20 +275,27 @@ __global__ void __launch_bounds__(512) k_bitonic_tile_merge(const BigSort b, int
 }
 
 // Segments of up to 128 entries (the bulk of every hierarchy: a handful of members with ~10
-// entries each): one WARP per segment, eight segments per CTA, warp-synchronous throughout.
-// Same three phases as k_gal_segment.  N = padded size of this launch's class (32, 64 or 128).
-__global__ void __launch_bounds__(256) k_gal_warp(const GalArgs g, int N, int nseg) {
-  extern __shared__ __align__(16) unsigned char gal_smem[];
+// entries each): one WARP per segment, eight segments per CTA, warp-synchronous throughout, and no
+// sort.  The first version sorted (coarse column, position) keys with a bitonic network in shared
+// memory and was issue-bound at ~2000 warp instructions per 40-entry segment (ncu,
+// profiles/r02_gal_warp.txt).  A segment has only a handful of distinct coarse columns, so: the
+// entries are staged by position (lane l keeps positions l, l + 32, ...), then the warp repeatedly
+// takes the smallest column still present (__reduce_min_sync) and hands it to the next lane; every
+// lane then adds the entries of its column in position order -- the member-then-CSR order of the
+// oracle, bit for bit.  Columns come out ascending.  K = padded size / 32 (1, 2 or 4).
+template <int K>
+__global__ void __launch_bounds__(256) k_gal_warp(const GalArgs g, int nseg) {
+  constexpr int N = 32 * K;
+  constexpr unsigned kFull = 0xffffffffu, kNone = 0xffffffffu;
+  __shared__ unsigned scol[8][N];
+  __shared__ double sval[8][N];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int sid = blockIdx.x * 8 + w;
   if (sid >= nseg) return;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(gal_smem) + (size_t)w * 2 * N;
-  double* vals = reinterpret_cast<double*>(keys + N);
   const int a = g.list[sid];
   const int p0 = g.Pptr[a], p1 = g.Pptr[a + 1];
   const int s0 = g.segoff[a];
   const int E = g.segoff[a + 1] - s0;
-  constexpr unsigned kFull = 0xffffffffu;
 
   // expand: 32 members at a time fetch their row descriptors together, then the rows are copied
   // one after the other with the descriptor broadcast by shuffle
@@ -306,56 +313,53 @@ __global__ void __launch_bounds__(256) k_gal_warp(const GalArgs g, int N, int ns
       const int qbase = __shfl_sync(kFull, base, q);
       for (int t = lane; t < qlen; t += 32) {
         const int e = qe0 + t;
-        keys[qbase + t] = ((unsigned long long)(unsigned)g.vA[g.J[e]] << 32) | (unsigned)(qbase + t);
-        vals[qbase + t] = g.W ? g.W[e] : 1.0;
+        scol[w][qbase + t] = (unsigned)g.vA[g.J[e]];
+        sval[w][qbase + t] = g.W ? g.W[e] : 1.0;
       }
     }
   }
-  for (int t = E + lane; t < N; t += 32) keys[t] = kPadKey;
   __syncwarp();
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int t = lane; t < N / 2; t += 32) {
-      const int hk = k >> 1;
-      const int lo = (t / hk) * k + (t % hk);
-      const int hi = lo ^ (k - 1);
-      const unsigned long long x = keys[lo], y = keys[hi];
-      if (x > y) {
-        keys[lo] = y;
-        keys[hi] = x;
-      }
-    }
-    __syncwarp();
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      for (int t = lane; t < N / 2; t += 32) {
-        const int lo = (t / j) * 2 * j + (t % j);
-        const int hi = lo + j;
-        const unsigned long long x = keys[lo], y = keys[hi];
-        if (x > y) {
-          keys[lo] = y;
-          keys[hi] = x;
-        }
-      }
-      __syncwarp();
-    }
+  unsigned col[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int pidx = k * 32 + lane;
+    col[k] = pidx < E ? scol[w][pidx] : kNone;
   }
-  int carry = 0;
-  for (int c0 = 0; c0 < E; c0 += 32) {
-    const int idx = c0 + lane;
-    const bool in = idx < E;
-    const unsigned col = in ? (unsigned)(keys[idx] >> 32) : 0u;
-    const bool head = in && (idx == 0 || (unsigned)(keys[idx - 1] >> 32) != col);
-    const unsigned mask = __ballot_sync(kFull, head);
-    if (head) {
-      const int rank = carry + __popc(mask & ((1u << lane) - 1u));
-      double sum = 0.0;
-      for (int r = idx; r < E && (unsigned)(keys[r] >> 32) == col; ++r)
-        sum += vals[(unsigned)(keys[r] & 0xffffffffu)];
-      g.tmpcol[s0 + rank] = (int)col;
-      g.tmpval[s0 + rank] = sum;
+  // Up to 32 distinct columns at a time, ascending: lane j keeps the j-th smallest still present.
+  // Then every lane adds the entries of ITS column in position order (all lanes read the same
+  // staged entry: shared-memory broadcasts), so a segment costs ~4 instructions per entry instead
+  // of a sort.
+  int nout = 0;
+  for (;;) {
+    unsigned my_col = kNone;
+    int found = 0;
+    for (; found < 32; ++found) {
+      unsigned mine = col[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) mine = min(mine, col[k]);
+      const unsigned cmin = __reduce_min_sync(kFull, mine);
+      if (cmin == kNone) break;
+      if (lane == found) my_col = cmin;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (col[k] == cmin) col[k] = kNone;
     }
-    carry += __popc(mask);
+    if (found == 0) break;
+    double sum = 0.0;
+#pragma unroll 4
+    for (int pidx = 0; pidx < E; ++pidx) {
+      const unsigned c = scol[w][pidx];
+      const double v = sval[w][pidx];
+      if (c == my_col) sum += v;  // member order, then CSR order: the oracle's sequence of additions
+    }
+    if (lane < found) {
+      g.tmpcol[s0 + nout + lane] = (int)my_col;
+      g.tmpval[s0 + nout + lane] = sum;
+    }
+    nout += found;
+    if (found < 32) break;
   }
-  if (lane == 0) g.count[a] = carry;
+  if (lane == 0) g.count[a] = nout;
 }
 
 // Exclusive scan of the row lengths on the device (three small kernels; m is at most a few million).
@@ -527,8 +531,12 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
     const int N = 32 << k;
     const int threads = std::max(32, std::min(512, N / 2));
     g.list = d_list.get() + class_begin[k];
-    if (N <= 128)
-      k_gal_warp<<<(cnt + 7) / 8, 256, (size_t)8 * N * 16, ctx->stream>>>(g, N, cnt);
+    if (N == 32)
+      k_gal_warp<1><<<(cnt + 7) / 8, 256, 0, ctx->stream>>>(g, cnt);
+    else if (N == 64)
+      k_gal_warp<2><<<(cnt + 7) / 8, 256, 0, ctx->stream>>>(g, cnt);
+    else if (N == 128)
+      k_gal_warp<4><<<(cnt + 7) / 8, 256, 0, ctx->stream>>>(g, cnt);
     else
       k_gal_segment<false><<<cnt, threads, (size_t)N * 16, ctx->stream>>>(g, N, 7);
     GE_CUDA(cudaGetLastError());
