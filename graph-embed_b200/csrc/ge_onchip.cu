@@ -20,10 +20,33 @@
 #include <cooperative_groups.h>
 
 #include "ge_onchip.cuh"
+#include "ge_tma.cuh"
 
 namespace ge {
 
 namespace {
+
+// ---- position exchange between the CTAs of a cluster without a cluster barrier -------------------
+// st.async writes one value into a peer's shared memory and completes its bytes on the PEER's
+// mbarrier; the receiver waits on its own mbarrier for the bytes of one iteration.  Measured
+// (tools/micro/latency.cu, 8 CTAs): 327 cycles per exchange against 684 for plain DSMEM stores +
+// barrier.cluster (whose arrive has to drain the stores first: ERRBAR was 20 % of the stall samples
+// of the cluster kernels).
+__device__ __forceinline__ uint32_t cluster_addr(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async(uint32_t dst, double v, uint32_t peer_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst),
+               "l"(__double_as_longlong(v)), "r"(peer_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async(uint32_t dst, float v, uint32_t peer_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+               "r"(__float_as_uint(v)), "r"(peer_bar)
+               : "memory");
+}
 
 // Shared-memory column records: positions are AoS with DP = 2 (d = 2) or 4 (d = 3, one pad) reals
 // per column, masses AoS (c, 1.5c, 1.875c, pad) in FP64 / (c) in FP32, so that one column is
@@ -367,12 +390,24 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
     if (NM > 1) ms[i * MP + (NM > 1 ? 1 : 0)] = (T)1.5 * c;
     if (NM > 2) ms[i * MP + (NM > 2 ? 2 : 0)] = (T)1.875 * c;
   }
+  __shared__ __align__(8) uint64_t xbar[2];  // one mbarrier per position buffer (exchange mode 1)
+  const bool async_x = a.exchange == 1;
+  if (tid == 0) {
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cluster.sync();  // also: nobody writes into a peer's shared memory before it is initialised
+  const uint32_t pos_addr = smem_addr(pos);
+  const uint32_t bar_addr[2] = {smem_addr(&xbar[0]), smem_addr(&xbar[1])};
+  const uint32_t xbytes = (uint32_t)s * D * (uint32_t)sizeof(T);
+  unsigned xphase = 0u;  // bit b: parity of the next completion of xbar[b]
 
   const T* pc = pos;
   T* pn = pos + S * DP;
   int nxt = 1;
   for (int it = 0; it < a.iters; ++it) {
+    if (async_x && tid == 0) mbar_expect_tx(&xbar[nxt], xbytes);  // this iteration's arrivals
     T f[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f[k] = (T)0;
@@ -447,17 +482,33 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
     if (!(a.debug_skip & 2)) vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
     if (owner) {  // the L lanes of the group share out the csize peer stores
       for (int rr = part; rr < csize; rr += L) {
-        T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+        if (async_x) {
+          const uint32_t dst = cluster_addr(pos_addr + (uint32_t)(((size_t)nxt * S + gv) * DP * sizeof(T)), rr);
+          const uint32_t pbar = cluster_addr(bar_addr[nxt], rr);
 #pragma unroll
-        for (int k = 0; k < D; ++k) dst[k] = x[k];
+          for (int k = 0; k < D; ++k) st_async(dst + k * (uint32_t)sizeof(T), x[k], pbar);
+        } else {
+          T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+#pragma unroll
+          for (int k = 0; k < D; ++k) dst[k] = x[k];
+        }
       }
     }
-    cluster.sync();
+    if (async_x) {
+      // every vertex's new position arrives through st.async: wait for this buffer's bytes.  No
+      // CTA can be more than one iteration ahead (it needs everybody's positions to go on), so the
+      // two buffers / barriers never see traffic of two different iterations.
+      mbar_wait(&xbar[nxt], (xphase >> nxt) & 1u);
+      xphase ^= 1u << nxt;
+    } else {
+      cluster.sync();
+    }
     const T* tmp = pc;
     pc = pn;
     pn = const_cast<T*>(tmp);
     nxt ^= 1;
   }
+  if (async_x) cluster.sync();  // nobody leaves while a peer may still be storing into it
 
   if (!a.normalize) {
     if (owner && part == 0) {
@@ -604,7 +655,18 @@ __global__ void __launch_bounds__(256) k_onchip_cluster2(const OnchipArgs<T> a, 
       atomicAdd(&Wm[lv * WS + a.e_idx[e]], ph.attract * w);
     }
   }
+  __shared__ __align__(8) uint64_t xbar[2];  // one mbarrier per position buffer (exchange mode 1)
+  const bool async_x = a.exchange == 1;
+  if (tid == 0) {
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cluster.sync();  // also: nobody writes into a peer's shared memory before it is initialised
+  const uint32_t pos_addr = smem_addr(pos);
+  const uint32_t bar_addr[2] = {smem_addr(&xbar[0]), smem_addr(&xbar[1])};
+  const uint32_t xbytes = (uint32_t)s * D * (uint32_t)sizeof(T);
+  unsigned xphase = 0u;
   const T* wrow = Wm + (owner ? lv : 0) * WS;
 
   const T* pc = pos;
@@ -616,6 +678,7 @@ __global__ void __launch_bounds__(256) k_onchip_cluster2(const OnchipArgs<T> a, 
   for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
   T grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
   for (int it = 0; it < a.iters; ++it) {
+    if (async_x && tid == 0) mbar_expect_tx(&xbar[nxt], xbytes);  // this iteration's arrivals
     T f0[D], f1[D], fa[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) f0[k] = f1[k] = fa[k] = (T)0;
@@ -717,23 +780,36 @@ __global__ void __launch_bounds__(256) k_onchip_cluster2(const OnchipArgs<T> a, 
     }
     if (owner) {  // the L lanes of the group share out the csize peer stores
       for (int rr = part; rr < csize; rr += L) {
-        T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+        if (async_x) {
+          const uint32_t dst = cluster_addr(pos_addr + (uint32_t)(((size_t)nxt * S + gv) * DP * sizeof(T)), rr);
+          const uint32_t pbar = cluster_addr(bar_addr[nxt], rr);
 #pragma unroll
-        for (int k = 0; k < D; ++k) dst[k] = x[k];
+          for (int k = 0; k < D; ++k) st_async(dst + k * (uint32_t)sizeof(T), x[k], pbar);
+        } else {
+          T* dst = cluster.map_shared_rank(pos, rr) + (size_t)nxt * S * DP + (size_t)gv * DP;
+#pragma unroll
+          for (int k = 0; k < D; ++k) dst[k] = x[k];
+        }
       }
     }
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    // between arrive and wait: what the next iteration needs from the vertex's own new position
+    if (!async_x) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // while the positions travel: what the next iteration needs from the vertex's own new position
     m2 = (T)0;
 #pragma unroll
     for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
     grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (async_x) {
+      mbar_wait(&xbar[nxt], (xphase >> nxt) & 1u);
+      xphase ^= 1u << nxt;
+    } else {
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     const T* tmp = pc;
     pc = pn;
     pn = const_cast<T*>(tmp);
     nxt ^= 1;
   }
+  if (async_x) cluster.sync();  // nobody leaves while a peer may still be storing into it
 
   if (!a.normalize) {
     if (owner && part == 0) {
@@ -1162,12 +1238,18 @@ void onchip_flat_t(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p
   a.normalize = p.normalize;
   a.ph = make_physics<T>(p);
   if (const char* v = std::getenv("GE_ONCHIP_SKIP")) a.debug_skip = std::atoi(v);
+  a.exchange = 1;  // st.async + mbarrier (0: DSMEM stores + cluster barrier)
+  if (const char* v = std::getenv("GE_K3_EXCHANGE")) a.exchange = std::atoi(v);
   // Larger coarsest levels are spread over a thread-block cluster (measured crossover n ~ 40).
   int csize = 1;
   if (!forces_only) {
-    csize = n >= 64 ? 8 : n >= 40 ? 4 : 1;
+    // measured with the st.async exchange (tools/k3_cluster_sweep.py, profiles/r02_k3_cluster_sweep.txt):
+    // one CTA up to ~30 vertices (n = 27: 0.68 us vs 0.85 on a cluster), 8 CTAs up to ~95
+    // (n = 34: 0.88 vs 1.09 on one CTA; n = 64: 0.94), the non-portable 16-CTA cluster beyond
+    // (n = 100: 1.36 vs 1.39; n = 200: 2.17 vs 2.54; d = 3 gains more)
+    csize = n >= 96 ? 16 : n >= 32 ? 8 : 1;
     if ((int64_t)nnz > (int64_t)16 * n && !a.ph.general_attraction && n <= 256)  // dense: see launch_onchip_cluster
-      csize = n >= 40 ? 8 : n >= 24 ? 4 : 1;
+      csize = n >= 32 ? 8 : n >= 24 ? 4 : 1;
     if (const char* v = std::getenv("GE_CLUSTER")) csize = std::atoi(v);
     csize = std::max(1, std::min(csize, 16));
   }

@@ -31,6 +31,7 @@ struct OnchipArgs {
   int forces_only = 0;
   int debug_skip = 0;                // measurement only (GE_ONCHIP_SKIP): 1 = no pair loop, 2 = no epilogue, 4 = no barrier
   int normalize = 0;                 // flat epilogue of include/forceatlas.hpp:272-303
+  int exchange = 0;                  // cluster kernels: 1 = st.async + mbarrier, 0 = DSMEM stores + cluster barrier
   Physics<T> ph;
 };
 

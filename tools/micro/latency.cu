@@ -67,6 +67,48 @@ __global__ void __cluster_dims__(8, 1, 1) k_cluster_store_bar(long long* cyc, in
   if (x == -1.0) cyc[1] = 0;
 }
 
+// The same exchange without a cluster barrier: every CTA sends its value to each peer with
+// st.async (the store itself completes bytes on the receiver's mbarrier), the receiver waits on its
+// own mbarrier for the 8 x 8 bytes of the iteration (two phases alternate with the two buffers).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __cluster_dims__(8, 1, 1) k_cluster_st_async(long long* cyc, int iters) {
+  __shared__ double buf[2][256];
+  __shared__ __align__(8) unsigned long long bar[2];
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = cl.block_rank();
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cl.sync();
+  long long t0 = clock64();
+  double x = threadIdx.x;
+  unsigned phase[2] = {0u, 0u};
+  for (int i = 0; i < iters; ++i) {
+    const int b = i & 1;
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 64;" ::"r"(smem_u32(&bar[b])) : "memory");
+    if (threadIdx.x < 8) {
+      unsigned dst, rbar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(&buf[b][rank])), "r"(threadIdx.x));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&bar[b])), "r"(threadIdx.x));
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                   ::"r"(dst), "l"(__double_as_longlong(x)), "r"(rbar) : "memory");
+    }
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(smem_u32(&bar[b])), "r"(phase[b]) : "memory");
+    phase[b] ^= 1u;
+    x += buf[b][(rank + 1) & 7];
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+  if (x == -1.0) cyc[1] = 0;
+  cl.sync();
+}
+
 __global__ void k_syncthreads(long long* cyc, int iters) {
   long long t0 = clock64();
   for (int i = 0; i < iters; ++i) __syncthreads();
@@ -107,6 +149,10 @@ int main() {
     k_cluster_store_bar<<<8, threads>>>(cyc, 10000);
     cudaDeviceSynchronize();
     printf("8 DSMEM stores + cluster.sync + LDS, %3d threads: %7.1f cycles\n", threads, double(cyc[0]) / 10000);
+    k_cluster_st_async<<<8, threads>>>(cyc, 10000);
+    cudaDeviceSynchronize();
+    printf("8 st.async stores + mbarrier wait + LDS, %3d threads: %7.1f cycles (%s)\n", threads,
+           double(cyc[0]) / 10000, cudaGetErrorString(cudaGetLastError()));
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
