@@ -406,6 +406,15 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
   const T* pc = pos;
   T* pn = pos + S * DP;
   int nxt = 1;
+  // own-position part of the step (:205-211): the gravity factor gravity * c_i / |x_i| needs only
+  // the vertex's own position, so it is formed while the new positions travel to the peers
+  T grav;
+  {
+    T m2 = (T)0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
+    grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
+  }
   for (int it = 0; it < a.iters; ++it) {
     if (async_x && tid == 0) mbar_expect_tx(&xbar[nxt], xbytes);  // this iteration's arrivals
     T f[D];
@@ -479,7 +488,27 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
 #pragma unroll
       for (int k = 0; k < D; ++k) f[k] += __shfl_xor_sync(0xffffffffu, f[k], off);
     }
-    if (!(a.debug_skip & 2)) vertex_step<T, D, false>(x, f, fprev, E, ci, ph);
+    if (!(a.debug_skip & 2)) {  // vertex_step<T, D, false> with the gravity factor prepared ahead
+      T sw2 = (T)0, f2 = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const T fk = fma(-x[k], grav, f[k]);
+        const T dk = fk - fprev[k];
+        sw2 = fma(dk, dk, sw2);
+        f2 = fma(fk, fk, f2);
+        f[k] = fk;
+      }
+      const T swing = sw2 > (T)0 ? sw2 * Real<T>::rsqrt_acc(sw2) : sw2;
+      const T ssw = swing > (T)0 ? swing * Real<T>::rsqrt_acc(swing) : swing;
+      T speed = ph.ks * ph.gspeed * Real<T>::rcp_acc((T)1 + ph.gspeed * ssw);
+      const T cap = ph.ksmax * Real<T>::rsqrt_acc(f2);
+      if (speed > cap) speed = cap;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        x[k] = fma(f[k], speed, x[k]);
+        fprev[k] = f[k];
+      }
+    }
     if (owner) {  // the L lanes of the group share out the csize peer stores
       for (int rr = part; rr < csize; rr += L) {
         if (async_x) {
@@ -493,6 +522,12 @@ __global__ void __launch_bounds__(512) k_onchip_cluster(const OnchipArgs<T> a, i
           for (int k = 0; k < D; ++k) dst[k] = x[k];
         }
       }
+    }
+    {  // while the positions travel: next iteration's gravity factor
+      T m2 = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) m2 = fma(x[k], x[k], m2);
+      grav = ph.gravity * ci * Real<T>::rsqrt_acc(m2);
     }
     if (async_x) {
       // every vertex's new position arrives through st.async: wait for this buffer's bytes.  No
