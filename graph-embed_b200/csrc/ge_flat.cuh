@@ -136,6 +136,7 @@ class RepulsionSymPlan {
   };
   ge_context* ctx_;
   int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0, rb_ = 1024;
+  bool half_ = false;  // 512-row blocks (256 threads x 2 rows): plans over many short segments
   int64_t ld_ = 0, reduce_len_ = 0;
   long long total_units_ = 0, pairs_ = 0;
   std::vector<PassDev> pass_;

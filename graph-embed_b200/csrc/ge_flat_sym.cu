@@ -140,16 +140,20 @@ __device__ __forceinline__ void sym_tile(const T* __restrict__ st, const T (&xi)
   }
 }
 
-template <int IPT>
+// Launch shapes: 1024 rows per block (512 threads x 2 rows, or 256 x 4) for long row ranges; HALF
+// blocks of 512 rows (256 threads x 2 rows) for plans over many short segments, where whole 1024-row
+// blocks waste lanes on padding rows and give too few units to share out evenly (R-MAT-20's large
+// aggregates: 1100 - 3800 rows each).
+template <int IPT, bool HALF>
 struct SymShape {
-  static constexpr int kThreads = IPT >= 4 ? 256 : 512;
+  static constexpr int kThreads = (IPT >= 4 || HALF) ? 256 : 512;
 };
 
-template <typename T, int D, int IPT, int CG>
-__global__ void __launch_bounds__(SymShape<IPT>::kThreads) k_repulsion_sym(const RepSymArgs<T> a) {
+template <typename T, int D, int IPT, int CG, bool HALF = false>
+__global__ void __launch_bounds__(SymShape<IPT, HALF>::kThreads) k_repulsion_sym(const RepSymArgs<T> a) {
   constexpr int TJ = kTileJ;
   constexpr int NA = D + 1;
-  constexpr int NW = SymShape<IPT>::kThreads / 32;
+  constexpr int NW = SymShape<IPT, HALF>::kThreads / 32;
   constexpr uint32_t kStageBytes = NA * TJ * sizeof(T);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tiles = reinterpret_cast<T*>(smem_raw);
@@ -335,13 +339,14 @@ int env_int(const char* name, int dflt) {
 }
 
 template <typename T, int D>
-const void* sym_kernel_d(int ipt, int cg) {
+const void* sym_kernel_d(int ipt, int cg, bool half) {
+  if (half) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8, true> : (const void*)k_repulsion_sym<T, D, 2, 4, true>;
   if (ipt >= 4) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 4, 8> : (const void*)k_repulsion_sym<T, D, 4, 4>;
   return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8> : (const void*)k_repulsion_sym<T, D, 2, 4>;
 }
 template <typename T>
-const void* sym_kernel(int dim, int ipt, int cg) {
-  return dim == 2 ? sym_kernel_d<T, 2>(ipt, cg) : sym_kernel_d<T, 3>(ipt, cg);
+const void* sym_kernel(int dim, int ipt, int cg, bool half) {
+  return dim == 2 ? sym_kernel_d<T, 2>(ipt, cg, half) : sym_kernel_d<T, 3>(ipt, cg, half);
 }
 template <typename T>
 size_t sym_smem(int dim, int threads) {
@@ -531,9 +536,16 @@ void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part
   // (25.8 vs 27.5; 32.1 vs 38.0); 8-column groups beat 4-column groups everywhere by 5-8 %
   ipt_ = env_int("GE_SYM_IPT", sizeof(T) == 8 ? 2 : 4) >= 4 ? 4 : 2;
   cg_ = env_int("GE_SYM_CG", 8) >= 8 ? 8 : 4;
-  threads_ = ipt_ >= 4 ? 256 : 512;
+  {  // half blocks when the segments are short on average (never for the flat sweep's one segment)
+    long long rows = 0;
+    for (const auto& sg : segments) rows += sg.row1 - sg.row0;
+    half_ = parts == 1 && segments.size() > 1 && rows < 4096LL * (long long)segments.size();
+    if (const char* e = std::getenv("GE_SYM_HALF")) half_ = std::atoi(e) != 0;
+    if (half_) ipt_ = 2;
+  }
+  threads_ = (ipt_ >= 4 || half_) ? 256 : 512;
   const int rb = threads_ * ipt_;
-  const void* fn = sym_kernel<T>(dim_, ipt_, cg_);
+  const void* fn = sym_kernel<T>(dim_, ipt_, cg_, half_);
   const size_t smem = sym_smem<T>(dim_, threads_);
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -625,7 +637,7 @@ void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2, T ou
     a.accumulate = first ? 0 : 1;
     if (pd.nblocks > 0 && pd.units > 0) {
       void* args[] = {(void*)&a};
-      GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_), dim3(pd.grid), dim3(threads_), args,
+      GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_, half_), dim3(pd.grid), dim3(threads_), args,
                                sym_smem<T>(dim_, threads_), ctx_->stream));
       ctx_->launches++;
     }

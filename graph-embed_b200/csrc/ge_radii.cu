@@ -436,11 +436,17 @@ __global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
         s_e[warp] = be;
       }
       __syncthreads();
-      if (tid == 0) {
-        for (int w = 1; w < NW; ++w) {
-          const double ot = s_t[w];
-          const int oi = s_i[w], oj = s_j[w];
-          const long long oe = s_e[w];
+      if (warp == 0) {  // the per-warp maxima meet in warp 0 (a serial scan by one thread cost ~1000 cycles per pop)
+        bt = lane < NW ? s_t[lane] : 0.0;
+        bi = lane < NW ? s_i[lane] : -1;
+        bj = lane < NW ? s_j[lane] : -1;
+        be = lane < NW ? s_e[lane] : -1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+          const long long oe = __shfl_xor_sync(0xffffffffu, be, off);
           const bool better = oe >= 0 && (be < 0 || ot > bt || (ot == bt && (oi > bi || (oi == bi && oj > bj))));
           if (better) {
             bt = ot;
@@ -449,6 +455,8 @@ __global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
             be = oe;
           }
         }
+      }
+      if (tid == 0) {
         int stop = 0, nf0 = -1, nf1 = -1;
         double nreach = 0.0;
         if (be < 0) {
