@@ -158,7 +158,9 @@ struct GrowArgs {
   long long E_base;
   int class_split;         // families with more events than this run in the wide kernel
   int batched;             // wide kernel: serve vertex-disjoint runs of events together (GE_RADII_BATCH=0: off)
+  int smem_events;         // wide kernel: stage a family's events in shared memory when they fit
 };
+constexpr int kRadiiSmemEvents = 8192;  // 16 bytes each: 128 KB of dynamic shared memory
 
 __device__ __forceinline__ bool key_greater(double t, int i, int j, double ot, int oi, int oj) {
   return t > ot || (t == ot && (i > oi || (i == oi && j > oj)));
@@ -177,7 +179,7 @@ __device__ __forceinline__ bool key_greater(double t, int i, int j, double ot, i
 // still growing in the reference, :640-642) return false untouched and take the one-pop-per-pass
 // loop below.
 template <int THREADS>
-__device__ bool grow_batched(const GrowArgs& g, const long long e0, const long long e1) {
+__device__ int grow_batched(const GrowArgs& g, double* evt, int2* evij, const long long e0, const long long e1) {
   constexpr int NW = THREADS / 32, CAP = 64, K = 16;
   __shared__ double w_t[NW];
   __shared__ int w_i[NW], w_j[NW], w_ok[NW];
@@ -187,29 +189,38 @@ __device__ bool grow_batched(const GrowArgs& g, const long long e0, const long l
   __shared__ double tau_t;
   __shared__ int tau_i, tau_j, cnt, firstconf, degenerate, nvalid;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) degenerate = 0;
+  __shared__ int n_batches, n_pops;
+  if (tid == 0) {
+    degenerate = 0;
+    n_batches = 0;
+    n_pops = 0;
+  }
   __syncthreads();
   for (bool first = true;; first = false) {
+    // Families where nearly every event touches one hub (stars) give batches of one: after 16
+    // batches averaging fewer than four pops the owed re-keys are applied once more and the
+    // one-pop-per-pass loop takes over (return 2).
+    const bool hand_over = n_batches >= 16 && n_pops < 4 * n_batches;  // (a batched pass costs ~3 one-pop passes)
     // ---- pass 1: owed re-keys, dead events, per-thread best --------------------------------------
     double bt = 0.0;
     int bi = -1, bj = -1;
     bool have = false, zero = false;
     for (long long e = e0 + tid; e < e1; e += THREADS) {
-      const int2 ij = g.ev_ij[e];
+      const int2 ij = evij[e];
       if (ij.x < 0) continue;
       const bool flag = ij.y < 0;  // key already carries one frozen end
       const int i = ij.x, j = flag ? ~ij.y : ij.y;
-      double t = g.ev_t[e];
+      double t = evt[e];
       const double ri = __ldcg(&g.r[i]), rj = __ldcg(&g.r[j]);
       const bool fi = ri > 0.0, fj = rj > 0.0;
       if (fi && fj) {
-        g.ev_ij[e] = make_int2(-1, -1);
+        evij[e] = make_int2(-1, -1);
         continue;
       }
       if ((fi || fj) && !flag) {
         t = -__dsub_rn(__dmul_rn(2.0, -t), fi ? ri : rj);
-        g.ev_t[e] = t;
-        g.ev_ij[e] = make_int2(i, ~j);
+        evt[e] = t;
+        evij[e] = make_int2(i, ~j);
       }
       zero |= t == 0.0;
       if (!have || key_greater(t, i, j, bt, bi, bj)) {
@@ -246,7 +257,8 @@ __device__ bool grow_batched(const GrowArgs& g, const long long e0, const long l
       firstconf = CAP;
     }
     __syncthreads();
-    if (first && degenerate) return false;  // nothing was modified: no ball is frozen yet
+    if (first && degenerate) return 0;  // nothing was modified: no ball is frozen yet
+    if (hand_over) return 2;            // every owed re-key has just been applied
     // ---- threshold: the K-th best of the per-warp maxima ---------------------------------------
     if (warp == 0) {
       const bool ok = lane < NW && w_ok[lane];
@@ -265,16 +277,16 @@ __device__ bool grow_batched(const GrowArgs& g, const long long e0, const long l
       }
     }
     __syncthreads();
-    if (nvalid == 0) return true;  // no live event left
+    if (nvalid == 0) return 1;  // no live event left
     // ---- pass 2: threads whose best reaches the threshold list their events at or above it -------
     const double tt = tau_t;
     const int ti = tau_i, tj = tau_j;
     if (have && !key_greater(tt, ti, tj, bt, bi, bj)) {
       for (long long e = e0 + tid; e < e1; e += THREADS) {
-        const int2 ij = g.ev_ij[e];
+        const int2 ij = evij[e];
         if (ij.x < 0) continue;
         const int i = ij.x, j = ij.y < 0 ? ~ij.y : ij.y;
-        const double t = g.ev_t[e];
+        const double t = evt[e];
         if (key_greater(tt, ti, tj, t, i, j)) continue;
         const int slot = atomicAdd(&cnt, 1);
         if (slot < CAP) {
@@ -302,10 +314,10 @@ __device__ bool grow_batched(const GrowArgs& g, const long long e0, const long l
       const int i1 = tau_i, j1 = tau_j;
       if (have && bt == t1 && bi == i1 && bj == j1) {
         for (long long e = e0 + tid; e < e1; e += THREADS) {
-          const int2 ij = g.ev_ij[e];
+          const int2 ij = evij[e];
           if (ij.x != i1) continue;
           const int j = ij.y < 0 ? ~ij.y : ij.y;
-          if (j != j1 || g.ev_t[e] != t1) continue;
+          if (j != j1 || evt[e] != t1) continue;
           l_t[0] = t1;
           l_i[0] = i1;
           l_j[0] = j1;
@@ -337,10 +349,14 @@ __device__ bool grow_batched(const GrowArgs& g, const long long e0, const long l
         }
     }
     __syncthreads();
+    if (tid == 0) {
+      n_batches += 1;
+      n_pops += min(n_list, firstconf);
+    }
     if (tid < min(n_list, firstconf)) {
       const int i = s_i[tid], j = s_j[tid];
       const double reach = -s_t[tid];
-      g.ev_ij[s_e[tid]] = make_int2(-1, -1);  // popped
+      evij[s_e[tid]] = make_int2(-1, -1);  // popped
       if (g.r[i] <= 0.0) g.r[i] = reach;
       if (g.r[j] <= 0.0) g.r[j] = reach;
     }
@@ -371,20 +387,43 @@ __global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
   }
   const long long E = e1 - e0;
   if ((E > g.class_split) != WIDE) return;
+  // Events of one family: in global memory, or -- for the wide kernel, when they fit -- staged in
+  // shared memory for the whole loop.  The hub families of power-law hierarchies are near-stars
+  // (R-MAT-20: 2 698 members, 7 661 events): one pop per pass, thousands of passes, each pass a few
+  // events per thread -- with the events in shared memory a pass costs a few hundred cycles
+  // instead of three dependent L2 round trips.
+  extern __shared__ __align__(16) unsigned char radii_smem[];
+  double* evt = g.ev_t;
+  int2* evij = g.ev_ij;
+  bool staged = false;
+  if (WIDE && E > 0 && E <= kRadiiSmemEvents && g.smem_events) {
+    double* st = reinterpret_cast<double*>(radii_smem);
+    int2* sij = reinterpret_cast<int2*>(st + kRadiiSmemEvents);
+    for (long long e = tid; e < E; e += THREADS) {
+      st[e] = g.ev_t[e0 + e];
+      sij[e] = g.ev_ij[e0 + e];
+    }
+    __syncthreads();
+    evt = st - e0;   // indexed with the same global event numbers below
+    evij = sij - e0;
+    staged = true;
+  }
+  (void)staged;
   const int s = c1 - c0;
   if (g.general && s == 0) return;
 
-  bool batched = false;
-  // Batching pays on mesh-like families (few events per member: consecutive events rarely share a
-  // vertex; Delaunay hierarchy 27 -> 11 ms per embed).  In the hub families of power-law graphs
-  // nearly every event touches the hub, batches have length one and the extra pass costs 20 %
-  // (R-MAT-20: 17 -> 21 ms), so those keep the one-pop-per-pass loop.
+  int batched = 0;  // 0: not run / declined, 1: finished, 2: handed over to the one-pop loop
+  // Batching pays on mesh-like families (consecutive events rarely share a vertex; Delaunay
+  // hierarchy 27 -> 11 ms per embed).  In the hub families of power-law graphs (near-stars) nearly
+  // every event touches the hub and batches have length one: grow_batched notices and hands over
+  // to the one-pop-per-pass loop.
   const long long members = g.general ? s : g.m_limit;
-  if (WIDE && !(g.general && s == 1) && E > 0 && g.batched && (g.batched > 1 || E <= 32 * members))
-    batched = grow_batched<THREADS>(g, e0, e1);
+  (void)members;
+  if (WIDE && !(g.general && s == 1) && E > 0 && g.batched)
+    batched = grow_batched<THREADS>(g, evt, evij, e0, e1);
   if (g.general && s == 1) {  // :687-691
     if (tid == 0) g.r[g.PJ[c0]] = g.rc[b];
-  } else if (E > 0 && !batched) {
+  } else if (E > 0 && batched != 1) {
     int f0 = -1, f1 = -1;
     double reach = 0.0;
     long long count = 0;
@@ -393,19 +432,20 @@ __global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
       int bi = -1, bj = -1;
       long long be = -1;
       for (long long e = e0 + tid; e < e1; e += THREADS) {
-        const int2 ij = g.ev_ij[e];
+        int2 ij = evij[e];
         if (ij.x < 0) continue;
-        double t = g.ev_t[e];
+        if (ij.y < 0) ij.y = ~ij.y;  // (flag of the batched loop: the key already carries one frozen end)
+        double t = evt[e];
         const bool hit0 = (ij.x == f0) | (ij.y == f0), hit1 = (ij.x == f1) | (ij.y == f1);
         if (hit0 | hit1) {  // a ball this event touches froze at the last pop (:655-676, :732-753)
           const int fz = hit0 ? f0 : f1;
           const int other = ij.x == fz ? ij.y : ij.x;
           t = -__dsub_rn(__dmul_rn(2.0, -t), reach);
           if (__ldcg(&g.r[other]) > 0.0) {  // both ends frozen: can never act again
-            g.ev_ij[e] = make_int2(-1, -1);
+            evij[e] = make_int2(-1, -1);
             continue;
           }
-          g.ev_t[e] = t;
+          evt[e] = t;
         }
         const bool better = be < 0 || t > bt || (t == bt && (ij.x > bi || (ij.x == bi && ij.y > bj)));
         if (better) {
@@ -462,7 +502,7 @@ __global__ void __launch_bounds__(THREADS) k_radii_grow(const GrowArgs g) {
         if (be < 0) {
           stop = 1;  // no live event left
         } else {
-          g.ev_ij[be] = make_int2(-1, -1);  // popped
+          evij[be] = make_int2(-1, -1);  // popped
           const bool live_i = g.r[bi] <= 0.0, live_j = g.r[bj] <= 0.0;
           if (live_i || live_j) {
             nreach = -bt;
@@ -540,7 +580,11 @@ void level_radii_device(ge_context* ctx, int m, int dim, double* d_x, double* d_
   {
     const char* e = std::getenv("GE_RADII_BATCH");
     g.batched = e ? std::atoi(e) : 1;
+    const char* e2 = std::getenv("GE_RADII_SMEM");
+    g.smem_events = e2 ? std::atoi(e2) : 1;
   }
+  const size_t wide_smem = (size_t)kRadiiSmemEvents * 16;
+  GE_CUDA(cudaFuncSetAttribute(k_radii_grow<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
   DevBuf<double> ev_t;
   DevBuf<int2> ev_ij;
   DevBuf<int> cnt, off, sums;
@@ -560,7 +604,7 @@ void level_radii_device(ge_context* ctx, int m, int dim, double* d_x, double* d_
     g.ev_ij = ev_ij.get();
     g.E_base = E;
     g.class_split = -1;  // always the wide kernel
-    k_radii_grow<1024, true><<<1, 1024, 0, st>>>(g);
+    k_radii_grow<1024, true><<<1, 1024, wide_smem, st>>>(g);
     GE_CUDA(cudaGetLastError());
     ctx->launches++;
   } else {
@@ -599,7 +643,7 @@ void level_radii_device(ge_context* ctx, int m, int dim, double* d_x, double* d_
     g.rc = d_rc;
     if (mc > 0) {
       k_radii_grow<64, false><<<mc, 64, 0, st>>>(g);
-      k_radii_grow<1024, true><<<mc, 1024, 0, st>>>(g);
+      k_radii_grow<1024, true><<<mc, 1024, wide_smem, st>>>(g);
       GE_CUDA(cudaGetLastError());
       ctx->launches += 2;
     }
