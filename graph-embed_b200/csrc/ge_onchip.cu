@@ -1091,6 +1091,7 @@ const void* cluster_kernel(int L) {
     case 2: return (const void*)k_onchip_cluster<T, D, 2, GA>;
     case 4: return (const void*)k_onchip_cluster<T, D, 4, GA>;
     case 16: return (const void*)k_onchip_cluster<T, D, 16, GA>;
+    case 32: return (const void*)k_onchip_cluster<T, D, 32, GA>;
     default: return (const void*)k_onchip_cluster<T, D, 8, GA>;
   }
 }
@@ -1169,9 +1170,12 @@ void launch_onchip_cluster(ge_context* ctx, const OnchipArgs<T>& a, int n, int d
   int L = 1;
   while (L < 8 && per_cta * (L * 2) <= 512) L *= 2;
   if (L == 8 && per_cta * 16 <= 128) L = 16;
+  // a full warp per vertex when that saves a trip of the pair loop (64 < n <= 128 on 16 CTAs:
+  // one trip of 4 columns per lane instead of two; n = 100: 1.34 -> 1.27 us, d = 3: 1.62 -> 1.51)
+  if (L == 16 && n > 64 && n <= 128 && per_cta * 32 <= 256) L = 32;
   if (const char* v = std::getenv("GE_ONCHIP_LANES")) {
     L = 1;
-    while (L < 16 && L * 2 <= std::atoi(v)) L *= 2;  // 1, 2, 4, 8 or 16
+    while (L < 32 && L * 2 <= std::atoi(v)) L *= 2;  // 1, 2, 4, 8, 16 or 32
   }
   while (L > 1 && per_cta * L > 512) L /= 2;
   const int threads = (int)round_up((int64_t)per_cta * L, 32);
