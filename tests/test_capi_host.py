@@ -144,3 +144,18 @@ def test_embed_aggregate_ranges_are_contiguous_and_balanced(capi, graphs):
             assert pairs == float((s * (s - 1)).sum())
             per = [cost[cuts[d]:cuts[d + 1]].sum() for d in range(ndev)]
             assert max(per) <= cost.sum() / ndev + cost.max() + 1e-9
+
+
+def test_multi_device_context_fails_loudly_without_gpus(capi):
+    """ge_context_create_multi has no fallback either: without a CUDA device it reports
+    GE_ERR_NO_DEVICE (on a GPU box with fewer devices than requested: GE_ERR_INVALID)."""
+    import ctypes as C
+    h = C.c_void_p()
+    st = capi.lib().ge_context_create_multi(2, None, C.byref(h))
+    assert st in (capi.GE_ERR_NO_DEVICE, capi.GE_ERR_INVALID, capi.GE_OK)
+    if st == capi.GE_OK:
+        assert capi.lib().ge_context_device_count(h) == 2
+        capi.lib().ge_context_destroy(h)
+    else:
+        assert not h.value and len(capi.lib().ge_last_error()) > 0
+    assert capi.lib().ge_context_device_count(None) == 0
