@@ -350,6 +350,8 @@ def run_ours(args):
             out["roofline_attraction_large"] = bench_attraction_large(args, capi, ctx, graphs, hbm_peak, hbm_src)
         if not args.no_embed:
             out["embed"] = bench_embed(args, capi, ctx, graphs)
+        if not args.no_embed:
+            out["embed_config1"] = bench_embed_config1(args, capi, ctx, graphs)
         if not args.no_embed and not args.no_refhier:
             out["embed_config3"] = bench_embed_refhier(args, capi, ctx, graphs)
         if not args.no_galerkin:
@@ -645,6 +647,39 @@ def bench_embed(args, capi, ctx, graphs):
             threads = host_threads()
             best = None
             for nt in sorted({1, threads}):
+                with stdout_to_stderr():
+                    _, secs = O.ref_embed(As, Ps, 2, seed=1, nthreads=nt, kind="fast")
+                if best is None or secs < best[0]:
+                    best = (secs, nt)
+            out["cpu_reference_embed_wall_s"], out["cpu_reference_threads"] = best
+    return out
+
+
+def bench_embed_config1(args, capi, ctx, graphs):
+    """BASELINE config 1 (configs[0], the reference's own CPU-runnable case): the pipeline of
+    examples/embedder.cpp on a 100 x 100 grid, coarsening 0.25, d = 2, hierarchy from the
+    reference's own partitioner (tests/golden/config1_grid100.npz); embed() wall time next to the
+    compiled reference on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import load_config1_golden
+    As, Ps, z = load_config1_golden(graphs)
+    ctx.embed(As, Ps, 2, seed=0, coarse_iterations=1000)  # warm-up
+    walls, st = [], None
+    for rep in range(3):
+        t = time.time()
+        x, st = ctx.embed(As, Ps, 2, seed=0)
+        walls.append(time.time() - t)
+    assert np.isfinite(x).all()
+    out = {"workload": "config1: 100x100 grid, coarsening 0.25, dim=2, hierarchy of the reference partitioner, "
+                       "levels %s" % [a.shape[0] for a in As],
+           "embed_wall_s": float(np.median(walls)), "coarse_ms": st["coarse_ms"], "levels_ms": st["levels_ms"],
+           "device_radii_ms": st["device_radii_ms"], "kernel_launches": st["kernel_launches"],
+           "pair_interactions": st["pair_interactions"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]}
+    if not args.no_cpu:
+        O = entry.load_oracle()
+        if O.ref_available("fast"):
+            best = None
+            for nt in sorted({1, host_threads()}):   # the reference is slower multi-threaded on small levels
                 with stdout_to_stderr():
                     _, secs = O.ref_embed(As, Ps, 2, seed=1, nthreads=nt, kind="fast")
                 if best is None or secs < best[0]:
