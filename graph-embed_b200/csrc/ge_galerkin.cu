@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "ge_context.h"
@@ -422,18 +424,68 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   const int nnz = A.indptr[n];
   const double t_begin = now_ms();
 
-  // host: vertex -> aggregate, segment offsets, row offsets inside the segments (O(n))
-  std::vector<int> vA(std::max(n, 1), -1), rowoff(std::max(n, 1), 0), segoff((size_t)m + 1, 0);
-  for (int a = 0; a < m; ++a) {
-    int run = 0;
-    for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) {
-      const int i = P.indices[c];
-      GE_REQUIRE(i >= 0 && i < n && vA[i] < 0, "P_T is not a partition of the vertices");
-      vA[i] = a;
-      rowoff[i] = run;
-      run += A.indptr[i + 1] - A.indptr[i];
+  // The fine graph does not depend on the layout: a helper thread uploads it (through the pinned
+  // staging ring when the caller's arrays are pageable) while this thread computes the layout.
+  const int64_t launches0 = ctx->launches;
+  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1));
+  DevBuf<double> d_W;
+  if (A.data != nullptr) d_W.alloc(ctx, std::max(nnz, 1));
+  ge_status up_status = GE_OK;
+  std::string up_error;
+  std::thread uploader([&] {
+    try {
+      GE_CUDA(cudaSetDevice(ctx->device));
+      d_I.upload(ctx, A.indptr, n + 1);
+      d_J.upload(ctx, A.indices, nnz);
+      if (A.data != nullptr) d_W.upload(ctx, A.data, nnz);
+    } catch (const Fail& f) {
+      up_status = f.st;
+      up_error = ge_last_error();
     }
-    segoff[a + 1] = segoff[a] + run;
+  });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } joiner{uploader};
+
+  // host: vertex -> aggregate, segment offsets, row offsets inside the segments (O(n)); the
+  // aggregates are independent, so a few threads share them out and a prefix sum follows
+  std::vector<int> vA(std::max(n, 1), -1), rowoff(std::max(n, 1), 0), segoff((size_t)m + 1, 0);
+  {
+    const int nt = m > (1 << 16) ? 8 : 1;
+    std::vector<int> bad(nt, 0);
+    auto part = [&](int t) {
+      const int a0 = (int)((int64_t)m * t / nt), a1 = (int)((int64_t)m * (t + 1) / nt);
+      for (int a = a0; a < a1; ++a) {
+        int run = 0;
+        for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c) {
+          const int i = P.indices[c];
+          if (i < 0 || i >= n) {
+            bad[t] = 1;
+            continue;
+          }
+          vA[i] = a;
+          rowoff[i] = run;
+          run += A.indptr[i + 1] - A.indptr[i];
+        }
+        segoff[a + 1] = run;  // length for now; prefix-summed below
+      }
+    };
+    if (nt == 1) {
+      part(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t) pool.emplace_back(part, t);
+      for (auto& th : pool) th.join();
+    }
+    bool ok = true;
+    for (int t = 0; t < nt; ++t) ok = ok && !bad[t];
+    // n entries in P_T, every one in range: all n vertices covered <=> none listed twice
+    for (int i = 0; ok && i < n; ++i) ok = vA[i] >= 0;
+    GE_REQUIRE(ok, "P_T is not a partition of the vertices");
+    for (int a = 0; a < m; ++a) segoff[a + 1] += segoff[a];
   }
   // size classes: padded power-of-two size 32 .. 4096 in shared memory, larger in global scratch
   constexpr int kClasses = 8;  // 32, 64, ..., 4096
@@ -470,20 +522,17 @@ int64_t galerkin(ge_context* ctx, const ge_csr& A, const ge_csr& P, int32_t* c_i
   const int big_begin = (int)all_list.size();
   all_list.insert(all_list.end(), big.begin(), big.end());
 
-  const int64_t launches0 = ctx->launches;
-  DevBuf<int> d_I(ctx, n + 1), d_J(ctx, std::max(nnz, 1)), d_vA(ctx, std::max(n, 1)),
-      d_Pptr(ctx, m + 1), d_Pidx(ctx, std::max(n, 1)), d_rowoff(ctx, std::max(n, 1)),
-      d_segoff(ctx, m + 1), d_list(ctx, std::max<size_t>(all_list.size(), 1)), d_count(ctx, std::max(m, 1)),
-      d_tmpcol(ctx, std::max(nnz, 1));
-  DevBuf<double> d_W, d_tmpval(ctx, std::max(nnz, 1)), d_gvals(ctx, (size_t)std::max<long long>(big_elems, 1));
+  uploader.join();  // (this thread issues CUDA calls from here on)
+  if (up_status != GE_OK) {
+    set_error("graph upload: " + up_error);
+    throw Fail{up_status};
+  }
+  DevBuf<int> d_vA(ctx, std::max(n, 1)), d_Pptr(ctx, m + 1), d_Pidx(ctx, std::max(n, 1)),
+      d_rowoff(ctx, std::max(n, 1)), d_segoff(ctx, m + 1), d_list(ctx, std::max<size_t>(all_list.size(), 1)),
+      d_count(ctx, std::max(m, 1)), d_tmpcol(ctx, std::max(nnz, 1));
+  DevBuf<double> d_tmpval(ctx, std::max(nnz, 1)), d_gvals(ctx, (size_t)std::max<long long>(big_elems, 1));
   DevBuf<unsigned long long> d_gkeys(ctx, (size_t)std::max<long long>(big_elems, 1));
   DevBuf<long long> d_bigoff(ctx, std::max<size_t>(bigoff.size(), 1));
-  d_I.upload(ctx, A.indptr, n + 1);
-  d_J.upload(ctx, A.indices, nnz);
-  if (A.data != nullptr) {
-    d_W.alloc(ctx, std::max(nnz, 1));
-    d_W.upload(ctx, A.data, nnz);
-  }
   d_vA.upload(ctx, vA.data(), n);
   d_Pptr.upload(ctx, P.indptr, m + 1);
   d_Pidx.upload(ctx, P.indices, n);
