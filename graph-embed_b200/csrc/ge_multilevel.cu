@@ -265,7 +265,19 @@ namespace {
 void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* v_A, bool forces_only,
                         int agg_begin, int agg_end, LevelLayout& L_, bool members = false) {
   const int m = P.rows;
-  const int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
+  int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
+  if (std::getenv("GE_CTA_MAX") == nullptr) {
+    // A SMALL multi-CTA tier is all launch overhead and pipeline fill (R-MAT-20 level 2: 28
+    // aggregates of 653 members, 1.9e7 pairs per iteration, took 20 ms of 3-launch iterations);
+    // its aggregates of up to 1024 members are better off with one persistent CTA each.  Large
+    // tiers keep the measured 512 limit (level 0 of the same hierarchy: 14.7 vs 21.2 ms).
+    double big_pairs = 0.0;
+    for (int a = agg_begin; a < agg_end; ++a) {
+      const double sz = P.indptr[a + 1] - P.indptr[a];
+      if (sz > cta_max) big_pairs += sz * (sz - 1);
+    }
+    if (big_pairs > 0.0 && big_pairs < 1e8) cta_max = kOnchipMaxVertices;
+  }
   std::vector<int4>& segs = L_.segs;
   std::vector<int4>& packs = L_.packs;
   CtaClass* cta_class = L_.cta_class;
