@@ -38,9 +38,12 @@ inline std::vector<std::vector<double>> run_embed(const std::vector<SparseMatrix
   opt.first_layer = index + 1;  // the reference numbers its progress lines from the finest level
   const int n = As[index].Rows();
   const int m = L > 0 ? As[index + 1].Rows() : 0;
-  std::vector<double> x(static_cast<size_t>(n) * d), rA(m), cA(static_cast<size_t>(m) * d);
+  // embedMultilevel's out-parameters (level index+1's radii and rescaled coordinates) are copied
+  // back from the device only when the caller asked for them: partition::embed downloads the
+  // finest coordinates alone
+  std::vector<double> x(static_cast<size_t>(n) * d), rA(r_A ? m : 0), cA(coords_A ? static_cast<size_t>(m) * d : 0);
   ge_b200::check(ge_embed(ge_b200::default_context(), L, a.data(), p.data(), d, &opt, x.data(),
-                          m ? rA.data() : nullptr, m ? cA.data() : nullptr, nullptr));
+                          (r_A && m) ? rA.data() : nullptr, (coords_A && m) ? cA.data() : nullptr, nullptr));
   if (r_A) *r_A = rA;
   if (coords_A) *coords_A = ge_b200::unflatten(cA, m, d);
   return ge_b200::unflatten(x, n, d);
