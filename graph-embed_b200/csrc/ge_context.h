@@ -133,8 +133,12 @@ class FlatSolver {
   ge_context* ctx = nullptr;
 };
 // part / parts: rank of a symmetric multi-rank solve (rows must be that rank's row block)
+// shared_deg: the row sums of every row (flat_degrees), computed once by a caller that builds
+// several plans of the same graph; nullptr: the plan computes them
 FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
-                             int row_begin, int row_end, int part = 0, int parts = 1);
+                             int row_begin, int row_end, int part = 0, int parts = 1,
+                             const double* shared_deg = nullptr);
+void flat_degrees(const ge_csr& A, const ge_params& p, std::vector<double>& deg);
 
 // ---- ge_onchip.cu ----------------------------------------------------------------------------
 // Small flat solve entirely inside one CTA (coarsest level: n ~ 30-100, 100 000 iterations).

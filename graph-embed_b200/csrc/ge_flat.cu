@@ -980,7 +980,7 @@ template <typename T>
 class FlatSolverT final : public FlatSolver {
  public:
   FlatSolverT(ge_context* c, const ge_csr& A, int dim, const ge_params& p, int rb, int re,
-              int part, int parts)
+              int part, int parts, const double* shared_deg)
       : n_(A.rows), dim_(dim), rb_(rb), re_(re), parts_(parts) {
     ctx = c;
     const bool verbose_ctor = std::getenv("GE_VERBOSE_PLAN") != nullptr;
@@ -1051,9 +1051,13 @@ class FlatSolverT final : public FlatSolver {
     lap("renumbering");
     // Vertex masses need every row's degree (include/forceatlas.hpp:127-140); rows outside the
     // owned block contribute nothing else.
-    std::vector<double> deg(n_);
+    std::vector<double> deg_own;
     const bool weighted = p.use_weights && A.data != nullptr;
-    {
+    if (reorder) shared_deg = nullptr;  // (the caller's row sums are in the caller's numbering)
+    if (shared_deg == nullptr) deg_own.resize(n_);
+    double* deg_w = deg_own.data();
+    const double* deg_r = shared_deg ? shared_deg : deg_own.data();
+    if (shared_deg == nullptr) {
       // row sums in CSR order (bit-identical whatever the thread count: rows are independent); a
       // few host threads on large graphs, where this pass is milliseconds of every plan creation
       auto rows = [&](int i0, int i1) {
@@ -1064,7 +1068,7 @@ class FlatSolverT final : public FlatSolver {
           } else {
             s = 1.0 * (I[i + 1] - I[i]);
           }
-          deg[i] = s;
+          deg_w[i] = s;
         }
       };
       const int nt = (weighted && I[n_] > (1 << 20)) ? 8 : 1;
@@ -1078,7 +1082,7 @@ class FlatSolverT final : public FlatSolver {
       }
     }
     DevBuf<double> d_deg(ctx, std::max(n_, 1));
-    d_deg.upload(ctx, deg.data(), n_);
+    d_deg.upload(ctx, deg_r, n_);
     mass_.alloc(ctx, (size_t)NM * ld_);
     k_mass_from_degree<T><<<(unsigned)((ld_ + 255) / 256), 256, 0, ctx->stream>>>(
         d_deg.get(), n_, ld_, NM, mass_.get());
@@ -1405,14 +1409,41 @@ class FlatSolverT final : public FlatSolver {
 }  // namespace
 
 FlatSolver* make_flat_solver(ge_context* ctx, const ge_csr& A, int dim, const ge_params& p,
-                             int row_begin, int row_end, int part, int parts) {
+                             int row_begin, int row_end, int part, int parts, const double* shared_deg) {
   GE_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
   GE_REQUIRE(A.rows == A.cols, "A must be square");
   GE_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= A.rows, "bad row block");
   GE_REQUIRE(parts >= 1 && part >= 0 && part < parts, "bad rank / world size");
   if (p.precision == GE_F32)
-    return new FlatSolverT<float>(ctx, A, dim, p, row_begin, row_end, part, parts);
-  return new FlatSolverT<double>(ctx, A, dim, p, row_begin, row_end, part, parts);
+    return new FlatSolverT<float>(ctx, A, dim, p, row_begin, row_end, part, parts, shared_deg);
+  return new FlatSolverT<double>(ctx, A, dim, p, row_begin, row_end, part, parts, shared_deg);
+}
+
+// include/forceatlas.hpp:127-140: weighted row sums (or row lengths) of every row, in CSR order; the
+// multi-device solve computes them once and hands them to every device's plan.
+void flat_degrees(const ge_csr& A, const ge_params& p, std::vector<double>& deg) {
+  const int n = A.rows;
+  deg.resize(std::max(n, 1));
+  const bool weighted = p.use_weights && A.data != nullptr;
+  auto rows = [&](int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {
+      double s = 0.0;
+      if (weighted) {
+        for (int e = A.indptr[i]; e < A.indptr[i + 1]; ++e) s += A.data[e];
+      } else {
+        s = 1.0 * (A.indptr[i + 1] - A.indptr[i]);
+      }
+      deg[i] = s;
+    }
+  };
+  const int nt = (weighted && A.indptr[n] > (1 << 20)) ? 8 : 1;
+  if (nt == 1) {
+    rows(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t) pool.emplace_back(rows, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
+  for (auto& th : pool) th.join();
 }
 
 }  // namespace ge

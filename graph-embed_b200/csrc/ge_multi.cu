@@ -187,6 +187,8 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
     t_mark = t;
   };
   std::vector<std::unique_ptr<FlatSolver>> solver(N);
+  std::vector<double> deg;  // every plan needs every row's mass: computed once, not once per device
+  flat_degrees(A, p, deg);
   std::vector<ge_status> status(N, GE_OK);
   std::vector<std::string> errors(N);
   {  // plan creation (graph upload, masses, scratch) and the coordinate upload: one host thread per device
@@ -196,7 +198,7 @@ void multi_flat_solve(ge_context* ctx, const ge_csr& A, int dim, double* coords,
         try {
           GE_CUDA(cudaSetDevice(M.dev[r]->device));
           const int rb = (int)std::min<int64_t>(n, r * R), re = (int)std::min<int64_t>(n, (r + 1) * R);
-          solver[r].reset(make_flat_solver(M.dev[r], A, dim, p, rb, re, r, N));
+          solver[r].reset(make_flat_solver(M.dev[r], A, dim, p, rb, re, r, N, deg.data()));
           GE_REQUIRE(solver[r]->symmetric(), "symmetric plan refused");
           solver[r]->upload_coords(coords);
           GE_CUDA(cudaStreamSynchronize(M.dev[r]->stream));
