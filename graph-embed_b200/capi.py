@@ -73,7 +73,7 @@ SYMBOLS = [
     "ge_flat_plan_bind_pair_sums", "ge_flat_plan_launch_repulsion", "ge_flat_plan_launch_step",
     "ge_flat_symmetric_share", "ge_galerkin", "ge_level_radii_device",
     "ge_context_create_multi", "ge_context_device_count",
-    "ge_flat_symmetric_pass_share", "ge_embed_aggregate_ranges",
+    "ge_flat_symmetric_pass_share", "ge_embed_aggregate_ranges", "ge_embed_aggregate_owners",
 ]
 
 _lib = None
@@ -369,6 +369,15 @@ def embed_aggregate_ranges(A, P_T, ndev):
     pairs = C.c_double()
     _check(lib().ge_embed_aggregate_ranges(a.ref(), p.ref(), int(ndev), _ptr(cuts, _pi), C.byref(pairs)))
     return cuts, pairs.value
+
+
+def embed_aggregate_owners(A, P_T, ndev):
+    """ge_embed_aggregate_owners -> (owner[m], ordered pairs per iteration) (host only)."""
+    a, p = CsrView(A), CsrView(P_T, with_data=False)
+    owner = np.zeros(max(P_T.shape[0], 1), dtype=np.int32)
+    pairs = C.c_double()
+    _check(lib().ge_embed_aggregate_owners(a.ref(), p.ref(), int(ndev), _ptr(owner, _pi), C.byref(pairs)))
+    return owner[:P_T.shape[0]], pairs.value
 
 
 class FlatPlan:

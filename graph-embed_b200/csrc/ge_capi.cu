@@ -461,6 +461,50 @@ double aggregate_ranges(const ge_csr& A, const ge_csr& P, int N, std::vector<int
   return pairs;
 }
 
+// The same as a set per device instead of a contiguous range: hierarchies of the reference
+// partitioner carry a few hundred giant aggregates (one of them can be a fifth of a device's share),
+// around which contiguous cuts are off by ~13 % (Delaunay 4M on 8 devices).  Heavy aggregates (cost
+// above 1/64 of a device's share) are placed largest-first on the least loaded device; the light
+// ones then fill the devices up in index order.  owned[d] is ascending.  Returns the ordered pairs.
+double aggregate_assignment(const ge_csr& A, const ge_csr& P, int N, std::vector<std::vector<int>>& owned) {
+  const int m = P.rows;
+  std::vector<double> cost((size_t)std::max(m, 1), 0.0);
+  double pairs = 0.0, total = 0.0;
+  for (int a = 0; a < m; ++a) {
+    const double s = P.indptr[a + 1] - P.indptr[a];
+    double nnz = 0.0;
+    for (int c = P.indptr[a]; c < P.indptr[a + 1]; ++c)
+      nnz += A.indptr[P.indices[c] + 1] - A.indptr[P.indices[c]];
+    pairs += s * (s - 1);
+    cost[a] = s * s + nnz;
+    total += cost[a];
+  }
+  owned.assign(N, std::vector<int>());
+  std::vector<double> load(N, 0.0);
+  const double heavy_min = total / N / 64.0;
+  std::vector<int> heavy;
+  for (int a = 0; a < m; ++a)
+    if (cost[a] >= heavy_min && cost[a] > 0.0) heavy.push_back(a);
+  std::stable_sort(heavy.begin(), heavy.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+  for (int a : heavy) {
+    int best = 0;
+    for (int d = 1; d < N; ++d)
+      if (load[d] < load[best]) best = d;
+    owned[best].push_back(a);
+    load[best] += cost[a];
+  }
+  const double target = total / N;
+  int d = 0;
+  for (int a = 0; a < m; ++a) {
+    if (cost[a] >= heavy_min && cost[a] > 0.0) continue;
+    while (d < N - 1 && load[d] >= target) ++d;
+    owned[d].push_back(a);
+    load[d] += cost[a];
+  }
+  for (auto& o : owned) std::sort(o.begin(), o.end());
+  return pairs;
+}
+
 // partition::embed on one device or, with a multi-device context, with the large levels sharded by
 // aggregates (aggregates are independent, include/forceatlas.hpp:340-341).
 struct EmbedRun {
@@ -481,6 +525,7 @@ struct EmbedRun {
     std::vector<std::unique_ptr<PrefetchedGraph>> pre;
     std::vector<DevBuf<double>> dx, dr;
     std::vector<int> a0, a1;
+    std::vector<std::vector<int>> owned;  // per sharded level: the aggregates this device solves
     std::thread prefetcher;
     std::string error;
     ge_status status = GE_OK;
@@ -503,19 +548,21 @@ struct EmbedRun {
       devs[d].dr.resize(L + 1);
       devs[d].a0.assign(L, 0);
       devs[d].a1.assign(L, 0);
+      devs[d].owned.assign(L, std::vector<int>());
     }
     const char* e = std::getenv("GE_SHARD_MIN_MPAIRS");
     const double min_pairs = 1e6 * (e ? std::atof(e) : 200.0);
     for (int l = 0; l < L; ++l) {
       devs[0].a1[l] = Ps[l].rows;
       if (N == 1) continue;
-      std::vector<int> cuts;
-      const double pairs = aggregate_ranges(As[l], Ps[l], N, cuts);
+      std::vector<std::vector<int>> sets;
+      const double pairs = aggregate_assignment(As[l], Ps[l], N, sets);
       if (pairs < min_pairs) continue;
       sharded[l] = 1;
       for (int d = 0; d < N; ++d) {
-        devs[d].a0[l] = cuts[d];
-        devs[d].a1[l] = cuts[d + 1];
+        devs[d].owned[l] = std::move(sets[d]);
+        devs[d].a0[l] = 0;
+        devs[d].a1[l] = (int)devs[d].owned[l].size();  // (only "has work" below; the set decides)
       }
     }
   }
@@ -555,7 +602,8 @@ struct EmbedRun {
             if (d != 0 && dev->a1[l] <= dev->a0[l]) continue;
             std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
             upload_graph(&side, A, *g);
-            g->layout = make_level_layout(&side, Ps[l], A.rows, dev->a0[l], dev->a1[l], d == 0);
+            g->layout = sharded[l] ? make_level_layout(&side, Ps[l], A.rows, 0, -1, d == 0, &dev->owned[l])
+                                   : make_level_layout(&side, Ps[l], A.rows, dev->a0[l], dev->a1[l], d == 0);
             GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
             GE_CUDA(cudaEventRecord(g->ready, side.stream));
             dev->pre[l] = std::move(g);
@@ -609,7 +657,8 @@ struct EmbedRun {
     const ge_csr& A = As[l];
     std::unique_ptr<PrefetchedGraph> g(new PrefetchedGraph);
     upload_graph(dev.ctx, A, *g);
-    g->layout = make_level_layout(dev.ctx, Ps[l], A.rows, dev.a0[l], dev.a1[l], d == 0);
+    g->layout = sharded[l] ? make_level_layout(dev.ctx, Ps[l], A.rows, 0, -1, d == 0, &dev.owned[l])
+                           : make_level_layout(dev.ctx, Ps[l], A.rows, dev.a0[l], dev.a1[l], d == 0);
     GE_CUDA(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
     GE_CUDA(cudaEventRecord(g->ready, dev.ctx->stream));
     dev.pre[l] = std::move(g);
@@ -668,8 +717,9 @@ struct EmbedRun {
     io.d_r_A = dev.dr[l + 1].get();
     io.keep_out = (l > 0 || sharded[l]) ? &dev.dx[l] : nullptr;
     io.download = host_out != nullptr;
+    io.owned = sharded[l] ? &dev.owned[l] : nullptr;
     multilevel_solve(dev.ctx, As[l], Ps[l], nullptr, nullptr, nullptr, init, host_out, dim, p, false,
-                     pairs, dev.a0[l], dev.a1[l], graph(d, l), &io);
+                     pairs, sharded[l] ? 0 : dev.a0[l], sharded[l] ? -1 : dev.a1[l], graph(d, l), &io);
   }
 
   // embedMultilevel, src/embed.cpp:576-796, unrolled from the coarsest level up.
@@ -1204,6 +1254,21 @@ ge_status ge_embed_aggregate_ranges(const ge_csr* A, const ge_csr* P_T, int32_t 
     std::vector<int> c;
     const double pairs = aggregate_ranges(*A, *P_T, ndev, c);
     for (int d = 0; d <= ndev; ++d) cuts[d] = c[d];
+    if (pairs_per_iteration) *pairs_per_iteration = pairs;
+  });
+}
+ge_status ge_embed_aggregate_owners(const ge_csr* A, const ge_csr* P_T, int32_t ndev, int32_t* owner,
+                                    double* pairs_per_iteration) {
+  return guarded([&] {
+    check_csr(A, "A");
+    check_csr(P_T, "P_T");
+    GE_REQUIRE(ndev >= 1 && owner != nullptr, "bad argument");
+    GE_REQUIRE(P_T->cols == A->rows && P_T->indptr[P_T->rows] == A->rows, "P_T must list every vertex once");
+    std::vector<std::vector<int>> sets;
+    const double pairs = aggregate_assignment(*A, *P_T, ndev, sets);
+    for (int a = 0; a < P_T->rows; ++a) owner[a] = -1;
+    for (int d = 0; d < ndev; ++d)
+      for (int a : sets[d]) owner[a] = d;
     if (pairs_per_iteration) *pairs_per_iteration = pairs;
   });
 }

@@ -153,7 +153,8 @@ void onchip_flat_solve(ge_context* ctx, const ge_csr& A, int dim, const ge_param
 // recorded after the last copy.
 struct LevelLayout;  // slot layout of a level (ge_multilevel.cu): depends on P_T only
 LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n, int agg_begin = 0,
-                               int agg_end = -1, bool members = true);
+                               int agg_end = -1, bool members = true,
+                               const std::vector<int>* owned = nullptr);
 void free_level_layout(LevelLayout* layout);
 struct PrefetchedGraph {
   DevBuf<int> I, J;
@@ -174,6 +175,7 @@ struct LevelIO {
   const double* d_r_A = nullptr;
   DevBuf<double>* keep_out = nullptr;
   bool download = true;
+  const std::vector<int>* owned = nullptr;  // solve exactly these aggregates (overrides the range)
 };
 void multilevel_solve(ge_context* ctx, const ge_csr& A, const ge_csr& P_T, const int32_t* v_A,
                       const double* coords_A, const double* r_A, const double* init,

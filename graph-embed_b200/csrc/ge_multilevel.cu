@@ -258,12 +258,21 @@ struct LevelLayout {
   double pairs = 0.0;
   DevBuf<int> d_vA, d_vtx, d_slot_of, d_agg_base, d_agg_of_slot;
   DevBuf<int> d_PI, d_PJ;  // the aggregation's CSR (member lists): the families of the radii step
-  int n = 0, m = 0, agg_begin = 0, agg_end = 0;
+  int n = 0, m = 0, agg_begin = 0, agg_end = 0, n_owned = -1;  // n_owned >= 0: an explicit aggregate set
 };
 
 namespace {
 void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* v_A, bool forces_only,
-                        int agg_begin, int agg_end, LevelLayout& L_, bool members = false) {
+                        int agg_begin, int agg_end, LevelLayout& L_, bool members = false,
+                        const std::vector<int>* owned = nullptr) {
+  // the aggregates this layout solves: a contiguous range, or (multi-device embed) an explicit set
+  auto for_each_aggregate = [&](auto&& body) {
+    if (owned != nullptr) {
+      for (int a : *owned) body(a);
+    } else {
+      for (int a = agg_begin; a < agg_end; ++a) body(a);
+    }
+  };
   const int m = P.rows;
   int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
   if (std::getenv("GE_CTA_MAX") == nullptr) {
@@ -272,10 +281,10 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
     // its aggregates of up to 1024 members are better off with one persistent CTA each.  Large
     // tiers keep the measured 512 limit (level 0 of the same hierarchy: 14.7 vs 21.2 ms).
     double big_pairs = 0.0;
-    for (int a = agg_begin; a < agg_end; ++a) {
+    for_each_aggregate([&](int a) {
       const double sz = P.indptr[a + 1] - P.indptr[a];
       if (sz > cta_max) big_pairs += sz * (sz - 1);
-    }
+    });
     if (big_pairs > 0.0 && big_pairs < 1e8) cta_max = kOnchipMaxVertices;
   }
   std::vector<int4>& segs = L_.segs;
@@ -285,14 +294,14 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   std::vector<int> by_size[33];
   std::vector<int> cta_aggs, grid_aggs;
   double pairs = 0.0;
-  for (int a = agg_begin; a < agg_end; ++a) {
+  for_each_aggregate([&](int a) {
     const int s = P.indptr[a + 1] - P.indptr[a];
     pairs += double(s) * double(s - 1);
-    if (s <= 0) continue;
+    if (s <= 0) return;
     if (s <= 32) by_size[s].push_back(a);
     else if (s <= cta_max) cta_aggs.push_back(a);
     else grid_aggs.push_back(a);
-  }
+  });
   L_.pairs = pairs;
   auto size_of = [&](int a) { return P.indptr[a + 1] - P.indptr[a]; };
   std::sort(cta_aggs.begin(), cta_aggs.end(), [&](int x, int y) { return size_of(x) > size_of(y); });
@@ -342,7 +351,7 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   const int64_t ld = round_up(std::max(L_.nslots, 1), kTileJ);
   L_.ld = ld;
   std::vector<int> vtx((size_t)ld, -1), slot_of(std::max(n, 1), -1), agg_of_slot((size_t)ld, -1);
-  for (int a = agg_begin; a < agg_end; ++a) {
+  for_each_aggregate([&](int a) {
     const int s = size_of(a);
     for (int i = 0; i < s; ++i) {
       const int v = P.indices[P.indptr[a] + i];
@@ -350,7 +359,7 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
       slot_of[v] = agg_base[a] + i;
       agg_of_slot[agg_base[a] + i] = a;
     }
-  }
+  });
 
   // the vertex -> aggregate map: the caller's, or derived from P_T
   std::vector<int32_t> vA_local;
@@ -380,6 +389,7 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   L_.m = m;
   L_.agg_begin = agg_begin;
   L_.agg_end = agg_end;
+  L_.n_owned = owned ? (int)owned->size() : -1;
   // (copies from pageable memory have left the host arrays when cudaMemcpyAsync returns)
 }
 
@@ -406,10 +416,13 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   // ---- slot layout (host + its device copies): prepared ahead of time or built here ----------
   LevelLayout own_layout;
   const LevelLayout* lay = (pre != nullptr && pre->layout != nullptr) ? pre->layout : nullptr;
+  const std::vector<int>* owned = io ? io->owned : nullptr;
   if (lay != nullptr)
-    GE_REQUIRE(lay->agg_begin == agg_begin && lay->agg_end == agg_end, "prepared layout covers another aggregate range");
+    GE_REQUIRE(owned ? lay->n_owned == (int)owned->size()
+                     : (lay->n_owned < 0 && lay->agg_begin == agg_begin && lay->agg_end == agg_end),
+               "prepared layout covers another set of aggregates");
   if (lay == nullptr) {
-    build_level_layout(ctx, P, n, v_A, forces_only, agg_begin, agg_end, own_layout);
+    build_level_layout(ctx, P, n, v_A, forces_only, agg_begin, agg_end, own_layout, false, owned);
     lay = &own_layout;
   }
   if (pairs_out) *pairs_out = lay->pairs;
@@ -470,7 +483,7 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   }
   d_eb.zero(ctx->stream);
   d_ee.zero(ctx->stream);
-  if (agg_begin > 0 || agg_end < m) d_out.zero(ctx->stream);  // rows of other ranks' aggregates
+  if (agg_begin > 0 || agg_end < m || owned != nullptr) d_out.zero(ctx->stream);  // rows of other ranks' aggregates
 
   lap("upload");
   // ---- prep --------------------------------------------------------------------------------
@@ -673,10 +686,10 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
 }  // namespace
 
 LevelLayout* make_level_layout(ge_context* ctx, const ge_csr& P_T, int n, int agg_begin, int agg_end,
-                               bool members) {
+                               bool members, const std::vector<int>* owned) {
   if (agg_end < 0) agg_end = P_T.rows;
   std::unique_ptr<LevelLayout> L(new LevelLayout);
-  build_level_layout(ctx, P_T, n, nullptr, false, agg_begin, agg_end, *L, members);
+  build_level_layout(ctx, P_T, n, nullptr, false, agg_begin, agg_end, *L, members, owned);
   return L.release();
 }
 void free_level_layout(LevelLayout* layout) { delete layout; }

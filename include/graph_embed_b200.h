@@ -251,6 +251,11 @@ int32_t ge_flat_symmetric_pass_share(int64_t ld, int32_t rank, int32_t world, in
  * cuts[ndev] = P_T->rows. */
 ge_status ge_embed_aggregate_ranges(const ge_csr* A, const ge_csr* P_T, int32_t ndev, int32_t* cuts,
                                     double* pairs_per_iteration);
+/* Host-only: the device (0 .. ndev-1) that solves each aggregate of a level in ge_embed on an
+ * ndev-device context: heavy aggregates largest-first on the least loaded device, light ones filled
+ * in index order.  owner: P_T->rows entries. */
+ge_status ge_embed_aggregate_owners(const ge_csr* A, const ge_csr* P_T, int32_t ndev, int32_t* owner,
+                                    double* pairs_per_iteration);
 /* 1 if the plan evaluates unordered pairs (ge_flat_plan_create chooses this for whole-graph plans
  * on large graphs), 0 for the ordered row-block sweep. */
 int32_t ge_flat_plan_is_symmetric(const ge_flat_plan* plan);

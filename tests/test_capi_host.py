@@ -159,3 +159,32 @@ def test_multi_device_context_fails_loudly_without_gpus(capi):
     else:
         assert not h.value and len(capi.lib().ge_last_error()) > 0
     assert capi.lib().ge_context_device_count(None) == 0
+
+
+def test_embed_aggregate_owners_balance_giant_aggregates(capi, graphs):
+    """Multi-device embed: every aggregate has exactly one owner, and with a few giant aggregates in
+    the level (the shape of the reference partitioner's hierarchies) the most loaded device is
+    within one light aggregate + the list-scheduling bound of the mean."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    sizes = np.concatenate([rng.integers(3000, 9000, 11), rng.integers(1, 12, 4000)])
+    rng.shuffle(sizes)
+    n = int(sizes.sum())
+    agg = np.repeat(np.arange(len(sizes)), sizes)
+    perm = rng.permutation(n)
+    agg = agg[np.argsort(perm)]
+    P = graphs.aggregation_matrix(agg.astype(np.int64), len(sizes))
+    P = sp.csr_matrix((P.data, P.indices.astype(np.int32), P.indptr.astype(np.int32)), shape=P.shape)
+    A = graphs.canonical(sp.identity(n, format="csr"))
+    cost = sizes.astype(np.float64) ** 2 + sizes
+    for ndev in (1, 2, 4, 8):
+        owner, pairs = capi.embed_aggregate_owners(A, P, ndev)
+        assert owner.min() >= 0 and owner.max() < ndev
+        assert pairs == float((sizes.astype(np.float64) * (sizes - 1)).sum())
+        load = np.bincount(owner, weights=cost, minlength=ndev)
+        # largest-first list scheduling: max load <= mean + largest job (and far better in practice)
+        assert load.max() <= cost.sum() / ndev + cost.max()
+        if ndev == 8:
+            cuts, _ = capi.embed_aggregate_ranges(A, P, ndev)
+            contiguous = max(cost[cuts[d]:cuts[d + 1]].sum() for d in range(ndev))
+            assert load.max() <= contiguous + 1e-9
