@@ -214,10 +214,13 @@ template <>
 struct Gather<double, 3> {
   static constexpr int DP = 4;
   __device__ __forceinline__ static void ld(const double* b, int j, double (&x)[3]) {
-    const double2 v = __ldg(reinterpret_cast<const double2*>(b) + 2 * j);
-    x[0] = v.x;
-    x[1] = v.y;
-    x[2] = __ldg(b + 4 * j + 2);
+    // one 256-bit load of the padded 32-byte record (sm_100: LDG.E.ENL2.256): a scattered gather
+    // pays one L1 wavefront per lane and instruction, so one instruction instead of LDG.128 + LDG.64
+    double pad;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(pad)
+        : "l"(b + 4 * (int64_t)j));
+    (void)pad;
   }
 };
 template <>
