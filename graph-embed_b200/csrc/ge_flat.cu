@@ -216,7 +216,7 @@ struct Gather<double, 3> {
   __device__ __forceinline__ static void ld(const double* b, int j, double (&x)[3]) {
     // one 256-bit load of the padded 32-byte record (sm_100: LDG.E.ENL2.256): a scattered gather
     // pays one L1 wavefront per lane and instruction, so one instruction instead of LDG.128 + LDG.64
-    double pad;
+    double pad __attribute__((unused));
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
         : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(pad)
         : "l"(b + 4 * (int64_t)j));
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256, MINB) k_attract_step_staged(const StepArg
 // (coalesced index / weight loads, 4 gathers in flight per thread), the partial sums are combined in
 // a fixed order (lane tree, then warps in order: bit-reproducible) and thread 0 finishes the row
 // exactly like the row kernels do.
-template <typename T, int D, bool GA, int kLongThreads>
+template <typename T, int D, bool GA, int kLongThreads, bool ML = false>
 __global__ void __launch_bounds__(kLongThreads) k_attract_step_long(const StepArgs<T> a,
                                                                     const int* __restrict__ rows) {
   __shared__ T red[D][kLongThreads / 32];
@@ -637,8 +637,10 @@ __global__ void __launch_bounds__(kLongThreads) k_attract_step_long(const StepAr
     fprev[k] = a.update ? a.Fprev[(int64_t)k * a.ldf + r] : (T)0;
     f[k] = acc + frep[k];
   }
-  const T E[D] = {};
-  vertex_step<T, D, false>(x, f, fprev, E, ci, a.ph);
+  T E[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) E[k] = (ML && a.Eext != nullptr) ? a.Eext[(int64_t)k * a.ldf + r] : (T)0;
+  vertex_step<T, D, ML>(x, f, fprev, E, ci, a.ph);
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     a.Fprev[(int64_t)k * a.ldf + r] = fprev[k];
@@ -942,13 +944,14 @@ void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int gro
 
 template <typename T>
 void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong,
-                              int threads) {
+                              int threads, bool ml) {
   if (nlong == 0) return;
   const bool ga = a.ph.general_attraction != 0;
   auto go = [&](auto d_c, auto ga_c) {
     constexpr int D = decltype(d_c)::value;
     constexpr bool GA = decltype(ga_c)::value;
-    if (threads >= 512) k_attract_step_long<T, D, GA, 512><<<nlong, 512, 0, ctx->stream>>>(a, rows);
+    if (ml) k_attract_step_long<T, D, GA, 128, true><<<nlong, 128, 0, ctx->stream>>>(a, rows);  // the multilevel tier
+    else if (threads >= 512) k_attract_step_long<T, D, GA, 512><<<nlong, 512, 0, ctx->stream>>>(a, rows);
     else k_attract_step_long<T, D, GA, 32><<<nlong, 32, 0, ctx->stream>>>(a, rows);
   };
   using std::integral_constant;
@@ -962,8 +965,8 @@ void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, co
   GE_CUDA(cudaGetLastError());
   ctx->launches++;
 }
-template void launch_attract_step_long<double>(ge_context*, const StepArgs<double>&, int, const int*, int, int);
-template void launch_attract_step_long<float>(ge_context*, const StepArgs<float>&, int, const int*, int, int);
+template void launch_attract_step_long<double>(ge_context*, const StepArgs<double>&, int, const int*, int, int, bool);
+template void launch_attract_step_long<float>(ge_context*, const StepArgs<float>&, int, const int*, int, int, bool);
 
 template void launch_attract_step<double>(ge_context*, const StepArgs<double>&, int, int, bool);
 template void launch_attract_step<float>(ge_context*, const StepArgs<float>&, int, int, bool);

@@ -136,7 +136,7 @@ class RepulsionSymPlan {
   };
   ge_context* ctx_;
   int dim_, threads_ = 256, ipt_ = 4, cg_ = 8, grid_ = 0, nblocks_ = 0, rb_ = 1024;
-  bool half_ = false;  // 512-row blocks (256 threads x 2 rows): plans over many short segments
+  int shrink_ = 0;  // 1: 512-row blocks (256 threads x 2 rows), 2: 256-row blocks: plans over many short segments
   int64_t ld_ = 0, reduce_len_ = 0;
   long long total_units_ = 0, pairs_ = 0;
   std::vector<PassDev> pass_;
@@ -181,10 +181,11 @@ struct StepArgs {
 // CSR attraction + gravity + step; `group` lanes per row; ml selects the multilevel clamps.
 template <typename T>
 void launch_attract_step(ge_context* ctx, const StepArgs<T>& a, int dim, int group, bool ml);
-// The rows listed in `rows` (local row indices, nlong of them), one CTA each (flat physics).
+// The rows listed in `rows` (local row indices, nlong of them), one CTA each; ml: the multilevel
+// clamps and external pull, 128 threads per row.
 template <typename T>
 void launch_attract_step_long(ge_context* ctx, const StepArgs<T>& a, int dim, const int* rows, int nlong,
-                              int threads);
+                              int threads, bool ml = false);
 
 int group_for_degree(double avg_deg);
 

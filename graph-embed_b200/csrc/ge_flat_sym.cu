@@ -140,20 +140,24 @@ __device__ __forceinline__ void sym_tile(const T* __restrict__ st, const T (&xi)
   }
 }
 
-// Launch shapes: 1024 rows per block (512 threads x 2 rows, or 256 x 4) for long row ranges; HALF
-// blocks of 512 rows (256 threads x 2 rows) for plans over many short segments, where whole 1024-row
-// blocks waste lanes on padding rows and give too few units to share out evenly (R-MAT-20's large
-// aggregates: 1100 - 3800 rows each).
-template <int IPT, bool HALF>
+// Launch shapes: 1024 rows per block (512 threads x 2 rows, or 256 x 4) for long row ranges.  Plans
+// over many short segments shrink the block: whole 1024-row blocks waste lanes on padding rows, give
+// too few units to share out evenly, and the part of a block on its segment's diagonal is swept in
+// full (every ordered pair), which costs rb/s extra for a segment of s rows.  SHRINK 1: 512 rows
+// (256 threads x 2), SHRINK 2: 256 rows (128 threads x 2, four CTAs per SM) -- R-MAT-20's large
+// aggregates hold 1100 - 3800 rows each.
+template <int IPT, int SHRINK>
 struct SymShape {
-  static constexpr int kThreads = (IPT >= 4 || HALF) ? 256 : 512;
+  static constexpr int kThreads = SHRINK == 2 ? 128 : (IPT >= 4 || SHRINK == 1) ? 256 : 512;
+  static constexpr int kMinBlocks = SHRINK == 2 ? 4 : SHRINK == 1 ? 2 : 0;  // 0: no constraint
 };
 
-template <typename T, int D, int IPT, int CG, bool HALF = false>
-__global__ void __launch_bounds__(SymShape<IPT, HALF>::kThreads) k_repulsion_sym(const RepSymArgs<T> a) {
+template <typename T, int D, int IPT, int CG, int SHRINK = 0>
+__global__ void __launch_bounds__(SymShape<IPT, SHRINK>::kThreads, SymShape<IPT, SHRINK>::kMinBlocks)
+    k_repulsion_sym(const RepSymArgs<T> a) {
   constexpr int TJ = kTileJ;
   constexpr int NA = D + 1;
-  constexpr int NW = SymShape<IPT, HALF>::kThreads / 32;
+  constexpr int NW = SymShape<IPT, SHRINK>::kThreads / 32;
   constexpr uint32_t kStageBytes = NA * TJ * sizeof(T);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* tiles = reinterpret_cast<T*>(smem_raw);
@@ -339,14 +343,15 @@ int env_int(const char* name, int dflt) {
 }
 
 template <typename T, int D>
-const void* sym_kernel_d(int ipt, int cg, bool half) {
-  if (half) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8, true> : (const void*)k_repulsion_sym<T, D, 2, 4, true>;
+const void* sym_kernel_d(int ipt, int cg, int shrink) {
+  if (shrink == 2) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8, 2> : (const void*)k_repulsion_sym<T, D, 2, 4, 2>;
+  if (shrink == 1) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8, 1> : (const void*)k_repulsion_sym<T, D, 2, 4, 1>;
   if (ipt >= 4) return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 4, 8> : (const void*)k_repulsion_sym<T, D, 4, 4>;
   return cg >= 8 ? (const void*)k_repulsion_sym<T, D, 2, 8> : (const void*)k_repulsion_sym<T, D, 2, 4>;
 }
 template <typename T>
-const void* sym_kernel(int dim, int ipt, int cg, bool half) {
-  return dim == 2 ? sym_kernel_d<T, 2>(ipt, cg, half) : sym_kernel_d<T, 3>(ipt, cg, half);
+const void* sym_kernel(int dim, int ipt, int cg, int shrink) {
+  return dim == 2 ? sym_kernel_d<T, 2>(ipt, cg, shrink) : sym_kernel_d<T, 3>(ipt, cg, shrink);
 }
 template <typename T>
 size_t sym_smem(int dim, int threads) {
@@ -536,16 +541,19 @@ void RepulsionSymPlan<T>::init(const std::vector<SymSegment>& segments, int part
   // (25.8 vs 27.5; 32.1 vs 38.0); 8-column groups beat 4-column groups everywhere by 5-8 %
   ipt_ = env_int("GE_SYM_IPT", sizeof(T) == 8 ? 2 : 4) >= 4 ? 4 : 2;
   cg_ = env_int("GE_SYM_CG", 8) >= 8 ? 8 : 4;
-  {  // half blocks when the segments are short on average (never for the flat sweep's one segment)
+  {  // smaller blocks when the segments are short on average (never for the flat sweep's one segment)
     long long rows = 0;
     for (const auto& sg : segments) rows += sg.row1 - sg.row0;
-    half_ = parts == 1 && segments.size() > 1 && rows < 4096LL * (long long)segments.size();
-    if (const char* e = std::getenv("GE_SYM_HALF")) half_ = std::atoi(e) != 0;
-    if (half_) ipt_ = 2;
+    const long long nseg = (long long)segments.size();
+    shrink_ = 0;
+    if (parts == 1 && nseg > 1) shrink_ = rows < 2048 * nseg ? 2 : rows < 4096 * nseg ? 1 : 0;
+    if (const char* e = std::getenv("GE_SYM_HALF")) shrink_ = std::atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("GE_SYM_SHRINK")) shrink_ = std::max(0, std::min(2, std::atoi(e)));
+    if (shrink_) ipt_ = 2;
   }
-  threads_ = (ipt_ >= 4 || half_) ? 256 : 512;
+  threads_ = shrink_ == 2 ? 128 : (ipt_ >= 4 || shrink_ == 1) ? 256 : 512;
   const int rb = threads_ * ipt_;
-  const void* fn = sym_kernel<T>(dim_, ipt_, cg_, half_);
+  const void* fn = sym_kernel<T>(dim_, ipt_, cg_, shrink_);
   const size_t smem = sym_smem<T>(dim_, threads_);
   if (smem > 48 * 1024)
     GE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -637,7 +645,7 @@ void RepulsionSymPlan<T>::launch(const T* pos, const T* mass, T* S, T eps2, T ou
     a.accumulate = first ? 0 : 1;
     if (pd.nblocks > 0 && pd.units > 0) {
       void* args[] = {(void*)&a};
-      GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_, half_), dim3(pd.grid), dim3(threads_), args,
+      GE_CUDA(cudaLaunchKernel(sym_kernel<T>(dim_, ipt_, cg_, shrink_), dim3(pd.grid), dim3(threads_), args,
                                sym_smem<T>(dim_, threads_), ctx_->stream));
       ctx_->launches++;
     }

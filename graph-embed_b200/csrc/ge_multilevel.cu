@@ -53,6 +53,13 @@ struct PrepArgs {
   int64_t ld;
   int nslots;
   int use_weights;
+  // rows of the large-aggregate tier (slots [0, grid_slots)) with more than long_len internal
+  // entries are listed for the CTA-per-row attraction kernel (power-law hierarchies: a hub keeps
+  // hundreds of neighbours inside its aggregate)
+  int grid_slots;
+  int long_len;
+  int* long_rows;
+  int* long_count;
 };
 
 // One warp per slot.
@@ -82,12 +89,27 @@ __global__ void __launch_bounds__(256) k_ml_prep(const PrepArgs<T> a) {
 #pragma unroll
   for (int k = 0; k < D; ++k) E[k] = 0.0;
   int cnt = 0;
-  for (int e0 = rb; e0 < re; e0 += 32) {
-    const int e = e0 + lane;
-    const bool valid = e < re;
-    const int j = valid ? a.J[e] : 0;
-    const double w = (valid && a.Dw != nullptr) ? a.Dw[e] : 1.0;
-    const int b = valid ? a.v_A[j] : -1;
+  // four 32-entry trips per pass: their index -> aggregate -> centre load chains are in flight
+  // together (a hub row of a power-law level has 1e5 entries and one warp)
+  constexpr int kTrips = 4;
+  for (int e00 = rb; e00 < re; e00 += 32 * kTrips) {
+    int jn[kTrips], bn[kTrips];
+    double wn[kTrips];
+#pragma unroll
+    for (int u = 0; u < kTrips; ++u) {
+      const int e = e00 + 32 * u + lane;
+      jn[u] = e < re ? a.J[e] : -1;
+      wn[u] = (e < re && a.Dw != nullptr) ? a.Dw[e] : 1.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kTrips; ++u) bn[u] = jn[u] >= 0 ? a.v_A[jn[u]] : -1;
+#pragma unroll
+    for (int u = 0; u < kTrips; ++u) {
+    if (e00 + 32 * u >= re) break;  // warp-uniform
+    const bool valid = jn[u] >= 0;
+    const int j = valid ? jn[u] : 0;
+    const double w = wn[u];
+    const int b = bn[u];
     const bool same = valid && b == agg;
     if (same) deg += a.use_weights ? w : 1.0;  // :366-369 / :376-379, self-loops included (Q5)
     // :417 compares the GLOBAL id j with the LOCAL index i (Q1): such an edge, and a self-loop,
@@ -112,6 +134,7 @@ __global__ void __launch_bounds__(256) k_ml_prep(const PrepArgs<T> a) {
       if (a.e_w) a.e_w[dst] = (T)w;
     }
     cnt += __popc(mask);
+    }
   }
   for (int off = 16; off > 0; off >>= 1) {
     deg += __shfl_xor_sync(0xffffffffu, deg, off);
@@ -127,6 +150,7 @@ __global__ void __launch_bounds__(256) k_ml_prep(const PrepArgs<T> a) {
     for (int k = 0; k < D; ++k) a.Eext[(int64_t)k * a.ld + slot] = (T)E[k];
     a.e_begin[slot] = rb;
     a.e_end[slot] = rb + cnt;
+    if (slot < a.grid_slots && cnt > a.long_len) a.long_rows[atomicAdd(a.long_count, 1)] = slot;
   }
 }
 
@@ -276,16 +300,18 @@ void build_level_layout(ge_context* ctx, const ge_csr& P, int n, const int32_t* 
   const int m = P.rows;
   int cta_max = std::min(env_int("GE_CTA_MAX", 512), kOnchipMaxVertices);
   if (std::getenv("GE_CTA_MAX") == nullptr) {
-    // A SMALL multi-CTA tier is all launch overhead and pipeline fill (R-MAT-20 level 2: 28
-    // aggregates of 653 members, 1.9e7 pairs per iteration, took 20 ms of 3-launch iterations);
-    // its aggregates of up to 1024 members are better off with one persistent CTA each.  Large
-    // tiers keep the measured 512 limit (level 0 of the same hierarchy: 14.7 vs 21.2 ms).
+    // A SMALL multi-CTA tier is all launch overhead and pipeline fill: below the size where the
+    // tier runs on the symmetric sweep (8e6 pairs per iteration) its aggregates of up to 1024
+    // members are better off with one persistent CTA each.  Above, the captured sweep + long-row
+    // attraction wins (R-MAT-20 level 2, 28 aggregates of 653 members, 1.9e7 pairs: 14.4 vs
+    // 16.3 ms), and large tiers keep the measured 512 limit anyway (level 0 of the same hierarchy:
+    // 14.7 vs 21.2 ms).
     double big_pairs = 0.0;
     for_each_aggregate([&](int a) {
       const double sz = P.indptr[a + 1] - P.indptr[a];
       if (sz > cta_max) big_pairs += sz * (sz - 1);
     });
-    if (big_pairs > 0.0 && big_pairs < 1e8) cta_max = kOnchipMaxVertices;
+    if (big_pairs > 0.0 && big_pairs < 1e6 * env_int("GE_ML_SYM_MIN_MPAIRS", 8)) cta_max = kOnchipMaxVertices;
   }
   std::vector<int4>& segs = L_.segs;
   std::vector<int4>& packs = L_.packs;
@@ -505,6 +531,14 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
   pa.ld = ld;
   pa.nslots = nslots;
   pa.use_weights = p.use_weights;
+  const int long_len = env_int("GE_ML_LONG_ROW", 128);
+  DevBuf<int> d_long_rows, d_long_count(ctx, 1);
+  d_long_count.zero(ctx->stream);
+  if (grid_slots > 0) d_long_rows.alloc(ctx, (size_t)grid_slots);
+  pa.grid_slots = long_len > 0 ? grid_slots : 0;
+  pa.long_len = long_len;
+  pa.long_rows = d_long_rows.get();
+  pa.long_count = d_long_count.get();
   d_mass.zero(ctx->stream);
   d_E.zero(ctx->stream);
   if (nslots > 0) {
@@ -606,6 +640,9 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
         rsegs.push_back(RowSegment{sg.x, sg.x + sg.y, sg.x, (int)round_up((int64_t)sg.x + sg.y, kTileJ)});
       rep.reset(new RepulsionPlan<T>(ctx, dim, rsegs));
     }
+    int nlong = 0;  // rows the prep kernel listed for the CTA-per-row attraction kernel
+    d_long_count.download(ctx, &nlong, 1);
+    GE_CUDA(cudaStreamSynchronize(ctx->stream));
     T* pos[2] = {d_pos0.get(), d_pos1.get()};
     int cur = 0;
     const int iters = forces_only ? 1 : p.iterations;
@@ -631,7 +668,9 @@ void multilevel_t(ge_context* ctx, const ge_csr& A, const ge_csr& P, const int32
       sa.nrows = grid_slots;
       sa.update = forces_only ? 0 : 1;
       sa.ph = oa.ph;
+      sa.long_threshold = nlong > 0 ? long_len : 0;
       launch_attract_step<T>(ctx, sa, dim, group, true);
+      launch_attract_step_long<T>(ctx, sa, dim, d_long_rows.get(), nlong, 128, true);
       if (!forces_only) cur ^= 1;
     };
     int it = 0;

@@ -8,7 +8,13 @@ entry.load_package()
 from graph_embed_b200 import capi, graphs
 kind = sys.argv[1] if len(sys.argv) > 1 else "delaunay"
 size = int(sys.argv[2]) if len(sys.argv) > 2 else (1_000_000 if kind == "delaunay" else 18)
-A = graphs.delaunay3d(size, seed=3) if kind == "delaunay" else graphs.largest_component(graphs.rmat(size, 16, seed=5))
+import scipy.sparse as sp
+cache = "/tmp/attr_heldout_%s_%d.npz" % (kind, size)  # several builds (GE_LIB) on one box: generate once
+if os.path.exists(cache):
+    A = sp.load_npz(cache)
+else:
+    A = graphs.delaunay3d(size, seed=3) if kind == "delaunay" else graphs.largest_component(graphs.rmat(size, 16, seed=5))
+    sp.save_npz(cache, A, compressed=False)
 n, nnz = A.shape[0], A.nnz
 pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6544.0
