@@ -599,7 +599,7 @@ def bench_galerkin(args, capi, ctx, graphs, hbm_peak, hbm_src):
     assert np.array_equal(C.indptr, As[1].indptr) and np.array_equal(C.indices, As[1].indices)
     assert np.array_equal(C.data, As[1].data)
     b = nnz * 12.0 + n * 16.0 + m * 12.0 + C.nnz * 12.0  # A once, row pointers / maps, A_c once
-    out = {"kernel": "k_gal_segment (+ k_gal_compact)", "bound": "hbm", "unit": "GB/s", "n": n, "m": m,
+    out = {"kernel": "k_gal_warp / k_gal_segment (+ scan, k_gal_compact)", "bound": "hbm", "unit": "GB/s", "n": n, "m": m,
            "nnz": nnz, "nnz_out": int(C.nnz), "device_ms": best["device_ms"], "total_ms": best["total_ms"],
            "bytes": b, "achieved": b / (best["device_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
            "peak_source": hbm_src, "entries_per_sec": nnz / (best["device_ms"] * 1e-3),

@@ -2,6 +2,7 @@
   compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
   compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
   compute-sanitizer --tool synccheck python tools/sanitize_smoke.py
+(compute-sanitizer is closed on the round-2 GPU pool: the script was run plain there.)
 Results are checked for finiteness only (parity is the test suite's job)."""
 import os
 import sys
