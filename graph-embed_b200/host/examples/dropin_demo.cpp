@@ -9,6 +9,7 @@
 #include <string>
 
 #include "embed.hpp"
+#include "export.hpp"
 
 namespace {
 
@@ -61,8 +62,11 @@ int flat_on_gpus(int gpus, int dimension) {
 }
 
 int main(int argc, char** argv) {
-  for (int a = 1; a + 1 < argc; ++a)
+  std::string outdir;  // --out DIR: write the layout and the plot inputs like examples/embedder.cpp:230-289
+  for (int a = 1; a + 1 < argc; ++a) {
     if (std::string(argv[a]) == "--gpus") return flat_on_gpus(std::atoi(argv[a + 1]), 2);
+    if (std::string(argv[a]) == "--out") outdir = argv[a + 1];
+  }
   int nx = argc > 1 ? std::atoi(argv[1]) : 64, ny = nx;
   const int dimension = argc > 2 ? std::atoi(argv[2]) : 2;
   std::vector<SparseMatrix> As = {grid(nx, ny)}, hierarchy;
@@ -98,5 +102,11 @@ int main(int argc, char** argv) {
       partition::embedVia(As, hierarchy, dimension, partition::forceAtlasMultilevelEmbedder());
   if (via.size() != coords.size()) return 2;
   std::cout << "embedVia ok: " << via.size() << " vertices" << std::endl;
+  if (!outdir.empty()) {
+    partition::writeCoords(coords, outdir + "/coords.txt");  // include/export.hpp:23
+    ge_b200::writePlotInputs(As[0], hierarchy, coords, dimension, outdir + "/part.temp",
+                             outdir + "/coords.temp", outdir + "/mat.temp");
+    std::cout << "wrote " << outdir << "/{coords.txt,part.temp,coords.temp,mat.temp}" << std::endl;
+  }
   return 0;
 }

@@ -296,6 +296,18 @@ def ref_galerkin(A, P_T, kind="strict"):
     return sp.csr_matrix((val[:nnz].copy(), idx[:nnz].copy(), ptr), shape=(m, m))
 
 
+def ref_write_coords(coords, path, kind="strict"):
+    """partition::writeCoords (src/export.cpp:27-39) of the compiled reference."""
+    x = _f64(coords)
+    ref_lib(kind).ref_write_coords(_p(x), int(x.shape[0]), int(x.shape[1]), str(path).encode())
+
+
+def ref_write_partition(part, path, kind="strict"):
+    """partition::writePartition (src/export.cpp:16-25) of the compiled reference."""
+    q = _i32(part)
+    ref_lib(kind).ref_write_partition(_p(q), int(q.shape[0]), str(path).encode())
+
+
 def ref_partition(A, coarsening_factor, matching_iterations=2, nthreads=8, kind="fast"):
     """partition::partition(A, cf, false, true, 1.0, matchingIterations, false) -> [P_T csr]."""
     import scipy.sparse as sp

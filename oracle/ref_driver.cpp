@@ -1,8 +1,8 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.
 //
 // extern "C" entry points around the reference's own functions, linked against
-// the reference's unmodified src/embed.cpp, src/partitioner.cpp and
-// src/matrixutils.cpp (compiled where they lie under /root/reference by
+// the reference's unmodified src/embed.cpp, src/partitioner.cpp,
+// src/matrixutils.cpp and src/export.cpp (compiled where they lie under /root/reference by
 // oracle/Makefile; outputs only in oracle/_ref/).  Loaded with ctypes by
 // tests/ and by bench.py's CPU-baseline / --impl reference legs.
 #include <omp.h>
@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "embed.hpp"
+#include "export.hpp"
 
 static unsigned g_seed = 0;
 extern "C" unsigned ge_ref_current_seed(void) { return g_seed; }
@@ -174,6 +175,17 @@ long ref_galerkin(int n, const int* I, const int* J, const double* D, int m, con
   std::memcpy(out_idx, C.GetIndices().data(), sizeof(int) * C.GetIndices().size());
   std::memcpy(out_val, C.GetData().data(), sizeof(double) * C.GetData().size());
   return (long)C.GetIndices().size();
+}
+
+// partition::writeCoords / writePartition (src/export.cpp:16-39) on caller-supplied arrays.
+void ref_write_coords(const double* x, int n, int d, const char* path) {
+  std::vector<std::vector<double>> coords(n, std::vector<double>(d));
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < d; k++) coords[i][k] = x[(size_t)i * d + k];
+  partition::writeCoords(coords, path);
+}
+void ref_write_partition(const int* part, int n, const char* path) {
+  partition::writePartition(std::vector<int>(part, part + n), path);
 }
 
 int ref_partition(int n, const int* I, const int* J, const double* D, double coarseningFactor,

@@ -2,6 +2,7 @@
 refuses to compute without a device, and its host-side level-driver step matches the oracle."""
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -188,3 +189,36 @@ def test_embed_aggregate_owners_balance_giant_aggregates(capi, graphs):
             cuts, _ = capi.embed_aggregate_ranges(A, P, ndev)
             contiguous = max(cost[cuts[d]:cuts[d + 1]].sum() for d in range(ndev))
             assert load.max() <= contiguous + 1e-9
+
+
+def test_export_header_writes_the_reference_formats(tmp_path):
+    """host/include/export.hpp: writePartition / writeCoords as src/export.cpp:16-39 writes them and
+    the three plot inputs of examples/embedder.cpp:230-289 (host-only, compiled here with g++)."""
+    src = tmp_path / "w.cpp"
+    src.write_text(r'''
+#include "export.hpp"
+int main(int, char** argv) {
+  const std::string d = argv[1];
+  std::vector<std::vector<double>> xy = {{0.5, -1.25}, {1e-7, 123456789.0}, {3.0, 1.0 / 3.0}};
+  partition::writeCoords(xy, d + "/coords.txt");
+  partition::writePartition({2, 0, 1}, d + "/part.txt");
+  SparseMatrix A({0, 1, 3, 4}, {1, 0, 2, 1}, {1.0, 1.0, 1.0, 1.0}, 3, 3);
+  SparseMatrix P({0, 2, 3}, {0, 1, 2}, {1.0, 1.0, 1.0}, 2, 3);
+  ge_b200::writePlotInputs(A, {P}, xy, 2, d + "/p.temp", d + "/c.temp", d + "/m.temp");
+  ge_b200::writePlotInputs(A, {}, {{1, 2, 3}, {4, 5, 6}, {7, 8, 9.5}}, 3, d + "/p0.temp", d + "/c0.temp", d + "/m0.temp");
+  return 0;
+}
+''')
+    exe = tmp_path / "w"
+    host = os.path.join(ROOT, "graph-embed_b200", "host")
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(host, "include"), "-I", os.path.join(host, "compat"),
+                           str(src), "-o", str(exe)])
+    subprocess.check_call([str(exe), str(tmp_path)])
+    xy = [[0.5, -1.25], [1e-7, 123456789.0], [3.0, 1.0 / 3.0]]
+    assert (tmp_path / "coords.txt").read_text() == "".join("".join("%g " % v for v in r) + "\n" for r in xy)
+    assert (tmp_path / "part.txt").read_text() == "2\n0\n1\n"
+    assert (tmp_path / "p.temp").read_text() == "3 1\n2 \n0 1 \n2 \n"
+    assert (tmp_path / "c.temp").read_text() == "".join("%g %g 0\n" % (r[0], r[1]) for r in xy)
+    assert (tmp_path / "m.temp").read_text() == "0 1\n1 0\n1 2\n2 1\n"
+    assert (tmp_path / "p0.temp").read_text() == "3 1\n3 \n0 \n1 \n2 \n"
+    assert (tmp_path / "c0.temp").read_text() == "1 2 3\n4 5 6\n7 8 9.5\n"

@@ -65,3 +65,46 @@ def test_galerkin_matches_the_callers_expression(ref, graphs):
     C, R = ref.galerkin(B, Ps[0]), ref.ref_galerkin(B, Ps[0])
     assert np.array_equal(C.indices, R.indices)
     assert np.abs(C.data - R.data).max() < 1e-12
+
+
+def test_export_writers_byte_identical(ref, tmp_path):
+    """host/include/export.hpp against the reference's own writeCoords / writePartition
+    (src/export.cpp:16-39, compiled into oracle/_ref): the files must be byte-identical."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "graph-embed_b200", "host")
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.normal(size=(200, 3)) * 10.0 ** rng.integers(-9, 9, size=(200, 1)),
+                        [[0.0, -0.0, 1.0], [1e-300, 1e300, 123456.5], [0.1, 1.0 / 3.0, 2.0 / 3.0]]])
+    part = rng.integers(0, 50, size=500).astype(np.int32)
+    x.tofile(tmp_path / "x.bin")
+    part.tofile(tmp_path / "p.bin")
+    src = tmp_path / "w.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdlib>
+#include "export.hpp"
+int main(int, char** argv) {
+  const std::string d = argv[1];
+  const int n = std::atoi(argv[2]), np_ = std::atoi(argv[3]);
+  std::vector<std::vector<double>> x(n, std::vector<double>(3));
+  FILE* f = std::fopen((d + "/x.bin").c_str(), "rb");
+  for (auto& r : x) if (std::fread(r.data(), 8, 3, f) != 3) return 1;
+  std::fclose(f);
+  std::vector<int> p(np_);
+  f = std::fopen((d + "/p.bin").c_str(), "rb");
+  if (std::fread(p.data(), 4, np_, f) != (size_t)np_) return 1;
+  std::fclose(f);
+  partition::writeCoords(x, d + "/ours_coords.txt");
+  partition::writePartition(p, d + "/ours_part.txt");
+  return 0;
+}
+''')
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(host, "include"), "-I", os.path.join(host, "compat"),
+                           str(src), "-o", str(tmp_path / "w")])
+    subprocess.check_call([str(tmp_path / "w"), str(tmp_path), str(x.shape[0]), str(part.shape[0])])
+    ref.ref_write_coords(x, tmp_path / "ref_coords.txt")
+    ref.ref_write_partition(part, tmp_path / "ref_part.txt")
+    assert (tmp_path / "ours_coords.txt").read_bytes() == (tmp_path / "ref_coords.txt").read_bytes()
+    assert (tmp_path / "ours_part.txt").read_bytes() == (tmp_path / "ref_part.txt").read_bytes()
