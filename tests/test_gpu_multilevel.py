@@ -79,6 +79,34 @@ def test_positions_after_k_iterations(ctx, capi, oracle, graphs, name, k, cta_ma
     assert np.abs(x - ref).max() < 1e-10, np.abs(x - ref).max()
 
 
+@pytest.mark.parametrize("name", ["rgg_big_aggs", "rmat"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_long_rows_of_the_segmented_tier(ctx, capi, oracle, graphs, name, dim, monkeypatch):
+    """Rows of the large-aggregate tier with many neighbours inside their aggregate (hubs of a
+    power-law level) are listed by the prep kernel and walked by one CTA each
+    (k_attract_step_long<.., ML>); GE_ML_LONG_ROW=4 sends every row with more than 4 internal
+    entries that way.  Forces and 3-iteration positions against the oracle, and the same
+    positions to rounding as without the tier (only the order of a row's partial sums changes)."""
+    monkeypatch.setenv("GE_CTA_MAX", "40")
+    As, Ps = _case(graphs, name)
+    A, P = As[0], Ps[0]
+    n, m = A.shape[0], P.shape[0]
+    rng = np.random.default_rng(7)
+    cA, rA = rng.normal(size=(m, dim)), rng.random(m) * 0.3 + 0.05
+    x = capi.reference_uniform(4, n * dim).reshape(n, dim)
+    init = oracle.multilevel_init(P, dim, 5)
+    _, F_ref, S = oracle.multilevel_run(A, P, cA, np.ones(m), dim, x, oracle.Params(iterations=1), forces_iter=0)
+    ref = oracle.multilevel_run(A, P, cA, rA, dim, init, oracle.Params(iterations=3))
+    out = {}
+    for long_row in ("4", "0"):
+        monkeypatch.setenv("GE_ML_LONG_ROW", long_row)
+        F = ctx.multilevel_forces(A, P, cA, x, dim, capi.multilevel_params())
+        assert force_error(F, F_ref, S).max() < TOL_F64, long_row
+        out[long_row] = ctx.multilevel_forceatlas(A, P, cA, rA, dim, capi.multilevel_params(iterations=3), init=init)
+        assert np.abs(out[long_row] - ref).max() < 1e-10, long_row
+    assert np.abs(out["4"] - out["0"]).max() < 1e-12
+
+
 def test_seeded_init_matches_reference_stream(ctx, capi, oracle):
     """init=NULL draws the reference's stream (forceatlas.hpp:341,356-358) from params.seed: the
     result equals the golden output of the COMPILED REFERENCE for the same seed (k=1,3)."""
